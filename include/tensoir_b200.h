@@ -1,0 +1,224 @@
+/* tensoir_b200 — C ABI of the B200-native TensoIR volume-rendering hot path.
+ *
+ * The reference (Haian-Jin/TensoIR) is 100 % Python/PyTorch and has no FFI of its own
+ * (SURVEY.md §8b); this ABI is what the Python shim in tensoir_b200/ binds with ctypes, and
+ * what a maintainer of the reference would bind from models/relight_utils.py and
+ * models/tensorBase_*.py (stubs in INTEGRATION.md).  Each entry point cites the reference
+ * function(s) it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (PyTorch); nothing is allocated,
+ *    freed or retained by the library; scratch buffers are passed in;
+ *  - all arithmetic is fp32, indices int32, counters uint64;
+ *  - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it;
+ *  - return value: 0 = ok, <0 = TirStatus argument error, >0 = cudaError_t passthrough;
+ *  - no global state, re-entrant, never throws.
+ */
+#ifndef TENSOIR_B200_H
+#define TENSOIR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TIR_ABI_VERSION 1
+
+typedef enum TirStatus {
+  TIR_OK = 0,
+  TIR_ERR_NULL = -1,      /* required pointer is NULL */
+  TIR_ERR_SHAPE = -2,     /* unsupported channel count / size */
+  TIR_ERR_CONFIG = -3,    /* bad enum / config value */
+  TIR_ERR_CAPACITY = -4   /* scratch buffer too small */
+} TirStatus;
+
+/* counters[] slots (uint64, accumulated with atomics; caller zeroes them) — parity and the
+ * roofline are both defined on these */
+enum {
+  TIR_CNT_MASK = 0,      /* in-bbox samples looked up in the alpha mask      (32 B each)   */
+  TIR_CNT_DENSITY = 1,   /* valid density samples                            (1152 B each) */
+  TIR_CNT_APP = 2,       /* appearance samples, weight > thres               (3456 B each) */
+  TIR_CNT_RAYS = 3,      /* rays marched (secondary: after the cosine test)               */
+  TIR_CNT_OVERFLOW = 4,  /* app samples dropped because the sample list was full (must be 0) */
+  TIR_CNT_SLOTS = 8
+};
+
+/* The VM field as the kernels see it: channel-last fp32 shadows of the reference's
+ * parameters (models/tensoRF_rotated_lights.py:11-29).
+ *   plane k  [G[m1]][G[m0]][C]  from density_plane[k] / app_plane[k]  ([1,C,G[m1],G[m0]])
+ *   line  k  [G[v]][C]          from density_line[k]  / app_line[k]   ([1,C,G[v],1])
+ * with matMode = {{0,1},{0,2},{1,2}}, vecMode = {2,1,0} (models/tensorBase_rotated_lights.py:398-399). */
+typedef struct TirField {
+  const float* dplane[3];
+  const float* dline[3];
+  const float* aplane[3];
+  const float* aline[3];
+  int32_t dC;              /* density channels per orientation (16)  — multiple of 4 */
+  int32_t aC;              /* appearance channels per orientation (48) — multiple of 4 */
+  int32_t grid[3];         /* gridSize x,y,z */
+  float aabb_lo[3];
+  float aabb_hi[3];
+  float inv_aabb[3];       /* 2/(hi-lo) exactly as the host computed it (tensorBase:612) */
+  /* alpha mask (AlphaGridMask, models/tensorBase_rotated_lights.py:100-119); amask == NULL => none */
+  const uint8_t* amask;    /* [Z][Y][X] 0/1 corner occupancy */
+  const uint8_t* acell;    /* [Z][Y][X] OR of the 8 corners of cell (x,y,z) (built by tir_pack_alpha_mask) */
+  int32_t agrid[3];        /* X,Y,Z */
+  float a_lo[3];
+  float a_inv[3];          /* 1/(hi-lo)*2 as AlphaGridMask.invgridSize */
+  float density_shift;     /* -10 */
+  float distance_scale;    /* 25 */
+  float weight_thres;      /* rayMarch_weight_thres 1e-4 */
+  int32_t softplus;        /* 1 = softplus(f+shift), 0 = relu(f) (tensorBase:813-817) */
+} TirField;
+
+/* A 3-layer MLP head (MLPRender_Fea / MLPBRDF_PEandFeature, tensorBase:122-146,:182-208) plus
+ * the shared basis_mat / light_line of TensorVMSplit.  Weights in PyTorch [out,in] row-major. */
+typedef struct TirMlp {
+  const float* w0; const float* b0;   /* [H, in_dim], [H]  in_dim = 2*pe_x*3 + 2*pe_f*F + 3 + F */
+  const float* w1; const float* b1;   /* [H, H], [H] */
+  const float* w2; const float* b2;   /* [out, H], [out] */
+  const float* basis;                 /* basis_mat.weight [F, 3*aC] */
+  const float* light_line;            /* light_line.weight [L, 3*aC]; NULL => no light factor (tensoRF_init) */
+  int32_t n_lights;
+  int32_t feat_dim;                   /* F = app_dim (27) */
+  int32_t hidden;                     /* featureC (128) */
+  int32_t out_dim;                    /* 3 or 4 */
+  int32_t pe_feat;                    /* fea_pe (2) */
+  int32_t pe_x;                       /* view_pe / pos_pe (2) */
+} TirMlp;
+
+typedef enum TirSampling {
+  TIR_SAMPLE_STEP = 0,   /* TensorBase.sample_ray (tensorBase:705-724): z = t_min + step*(i + jitter) */
+  TIR_SAMPLE_TABLE = 1   /* sample_ray_equally (relight_utils.py:707-722): z = z_table[i], same for all rays */
+} TirSampling;
+
+typedef struct TirMarchCfg {
+  int32_t sampling;        /* TirSampling */
+  int32_t n_samples;
+  float step;              /* stepSize (STEP) */
+  float near;              /* near_far[0] (STEP: clamp of t_min) */
+  float far;
+  const float* z_table;    /* [n_samples] (TABLE), computed by the host exactly like the reference */
+  const float* jitter;     /* [n_rays] per-ray jitter or NULL (STEP; the reference draws it on the CPU, tensorBase:717) */
+  int32_t flags;           /* TIR_MARCH_NO_BBOX: skip the in-aabb test (filtering_rays samples the alpha mask for every
+                              point, tensorBase:803-804) */
+} TirMarchCfg;
+
+enum { TIR_MARCH_NO_BBOX = 1 };
+
+/* One compacted appearance sample produced by the march (w > weight_thres), consumed by tir_app_mlp. */
+typedef struct TirAppSample {
+  float xn[3];             /* normalised coords in [-1,1] */
+  float weight;
+  int32_t ray;
+  int32_t sample;          /* index along the ray */
+} TirAppSample;
+
+int tir_abi_version(void);
+
+/* NCHW [1,C,H,W] parameter -> channel-last [H][W][C] shadow. Replaces nothing in the reference:
+ * it is the layout change that makes one bilinear tap one contiguous 4*C-byte read. */
+int tir_pack_channels_last(const float* nchw, float* out, int32_t C, int32_t H, int32_t W, void* stream);
+/* inverse scatter of a channel-last gradient back to NCHW (accumulating: nchw += cl) */
+int tir_unpack_channels_last_add(const float* cl, float* nchw, int32_t C, int32_t H, int32_t W, void* stream);
+
+/* float alpha_volume [Z,Y,X] (0/1) -> corner bytes + per-cell OR bytes (AlphaGridMask, tensorBase:100-119). */
+int tir_pack_alpha_mask(const float* volume, uint8_t* corners, uint8_t* cells,
+                        int32_t X, int32_t Y, int32_t Z, void* stream);
+
+/* compute_densityfeature + feature2density on normalised points
+ * (models/tensoRF_rotated_lights.py:95-110, tensorBase:813-817): xn [n,3] -> feature [n], sigma [n]
+ * (either output may be NULL). */
+int tir_density_points(const TirField* field, const float* xn, int64_t n, float* feature, float* sigma, void* stream);
+
+/* AlphaGridMask.sample_alpha(xyz) > 0 on world-space points (tensorBase:112-116): xyz [n,3] -> mask [n] (0/1). */
+int tir_alpha_mask_points(const TirField* field, const float* xyz, int64_t n, uint8_t* mask, void* stream);
+
+/* Density-only march: sample_ray / sample_ray_equally + alpha-mask filter + compute_densityfeature +
+ * feature2density + raw2alpha + compositing.  Replaces compute_transmittance
+ * (models/relight_utils.py:657-705) and the density half of TensorBase.forward (tensorBase:885-921,:974-975).
+ *   rays_o, rays_d [n_rays,3];  t_last [n_rays] (= nerv_vis), acc [n_rays] (nerfactor_vis = 1-acc),
+ *   depth [n_rays] (sum w*z) — any output may be NULL. */
+int tir_march_density(const TirField* field, const float* rays_o, const float* rays_d, int64_t n_rays,
+                      const TirMarchCfg* cfg, float* t_last, float* acc, float* depth,
+                      uint64_t* counters, void* stream);
+
+/* Full radiance march over explicit rays: compute_radiance (models/relight_utils.py:777-834) and, with
+ * TIR_SAMPLE_STEP, the rgb half of TensorBase_Init.forward (models/tensorBase_init.py:406-462).
+ *   light_idx [n_rays] int32 or NULL; view direction fed to the MLP = rays_d.
+ *   samples: scratch list [capacity] of TirAppSample; sample_count: device uint32 (caller zeroes).
+ *   rgb [n_rays,3] must be zeroed by the caller (accumulated with atomics). */
+int tir_march_radiance(const TirField* field, const TirMlp* mlp, const float* rays_o, const float* rays_d,
+                       const int32_t* light_idx, int64_t n_rays, const TirMarchCfg* cfg,
+                       float* t_last, float* acc, float* depth, float* rgb,
+                       TirAppSample* samples, uint32_t* sample_count, int64_t capacity,
+                       uint64_t* counters, void* stream);
+
+/* Secondary shading of render_with_BRDF (models/relight_utils.py:428-450): for every surface point p and
+ * every incident direction d with clamp(d.n,0) > 1e-6, march compute_radiance along (p, d).
+ * Rays are generated on chip (no [bs,n_dirs,3] tensors).
+ *   surf_xyz, normals [n_pts,3]; light_idx [n_pts]; dirs [n_dirs,3]
+ *   vis [n_pts,n_dirs] (T_last, 0 where masked), indirect [n_pts,n_dirs,3] (caller zeroes both). */
+int tir_secondary_radiance(const TirField* field, const TirMlp* mlp, const float* surf_xyz, const float* normals,
+                           const int32_t* light_idx, int64_t n_pts, const float* dirs, int32_t n_dirs,
+                           const TirMarchCfg* cfg, float* vis, float* indirect,
+                           TirAppSample* samples, uint32_t* sample_count, int64_t capacity,
+                           uint64_t* counters, void* stream);
+
+/* Appearance gather + basis_mat + MLPRender_Fea on a compacted sample list
+ * (compute_appfeature tensoRF_rotated_lights.py:197-224 + MLPRender_Fea tensorBase:136-146):
+ *   rgb_out[ray] += weight * sigmoid(mlp(...)) for every sample; dirs_of_ray gives the view dir.
+ *   ray_dirs [n_rays,3] when dir_stride_rays = 1, or the [n_dirs,3] table with ray % n_dirs indexing
+ *   when n_dirs > 0.  light_idx indexed by ray (n_dirs == 0) or by ray / n_dirs. */
+int tir_app_mlp(const TirField* field, const TirMlp* mlp, const TirAppSample* samples,
+                const uint32_t* sample_count, int64_t max_samples, const float* ray_dirs, int32_t n_dirs,
+                const int32_t* light_idx, float* rgb_out, void* stream);
+
+/* Same gather+MLP on explicit points (no compositing): xn [n,3] normalised coords, x_in [n,3] the 3-vector fed
+ * to the MLP next to the features (view dir for MLPRender_Fea, position for MLPBRDF_PEandFeature),
+ * light_idx [n] or NULL (row 0 of mlp->light_line, e.g. the mean-light row of compute_intrinfeature),
+ * act 0 = sigmoid, 1 = tanh -> out [n,out_dim].  Mirrors renderModule*(compute_*feature(...)). */
+int tir_app_mlp_points(const TirField* field, const TirMlp* mlp, const float* xn, const float* x_in,
+                       const int32_t* light_idx, int64_t n, int32_t act, float* out, void* stream);
+
+/* ---- modular, autograd-facing half of the primary march (training needs gradients) --------------------- */
+
+/* plane*line products of the appearance tensors on normalised points: xn [n,3] -> out [n, 3*aC]
+ * (first half of compute_{app,both,intrin}feature, models/tensoRF_rotated_lights.py:141-153). */
+int tir_vm_app_products(const TirField* field, const float* xn, int64_t n, float* out, void* stream);
+/* backward of the above into channel-last gradient shadows g_plane[k] [H][W][aC], g_line[k] [D][aC] (accumulating;
+ * replaces grid_sampler_2d_backward). */
+int tir_vm_app_products_bwd(const TirField* field, const float* xn, int64_t n, const float* g_out,
+                            float* const* g_plane, float* const* g_line, void* stream);
+/* backward of tir_density_points' feature output (compute_densityfeature, tensoRF:95-110). */
+int tir_vm_density_bwd(const TirField* field, const float* xn, int64_t n, const float* g_feature,
+                       float* const* g_plane, float* const* g_line, void* stream);
+/* density feature and its analytic spatial gradient d f / d x_hat [n,3] with the clamped-index sampler
+ * (compute_densityfeature_with_xyz_grad tensoRF:113-129 + grid_sample relight_utils.py:57-107; feeds
+ * compute_derived_normals tensorBase:839-856 without an autograd.grad round trip). */
+int tir_vm_density_grad(const TirField* field, const float* xn, int64_t n, float* feature, float* dfdx, void* stream);
+/* backward of both outputs (g_feature / g_dfdx may be NULL) — the reference's double backward. */
+int tir_vm_density_grad_bwd(const TirField* field, const float* xn, int64_t n, const float* g_feature,
+                            const float* g_dfdx, float* const* g_plane, float* const* g_line, void* stream);
+
+/* sample_ray + in-bbox + alpha-mask filter (tensorBase:705-724, :892-897) as a ray-sorted list, two passes:
+ * count -> (host cumsum) -> fill.  Row order equals the reference's xyz_sampled[ray_valid]. */
+int tir_valid_samples_count(const TirField* field, const float* rays_o, const float* rays_d, int64_t n_rays,
+                            const TirMarchCfg* cfg, int32_t* counts, uint64_t* counters, void* stream);
+int tir_valid_samples_fill(const TirField* field, const float* rays_o, const float* rays_d, int64_t n_rays,
+                           const TirMarchCfg* cfg, const int64_t* offsets, int32_t* out_ray, int32_t* out_sample,
+                           float* out_xn, float* out_z, float* out_dist, void* stream);
+
+/* raw2alpha (tensorBase:21-28) over ray segments of a valid-sample list, sequential like torch.cumprod:
+ * weight[i] = alpha_i * T_i, trans[i] = T_i (exclusive), t_last[ray]. */
+int tir_composite_fwd(const float* sigma, const float* dist, const int64_t* offsets, int64_t n_rays,
+                      float distance_scale, float* weight, float* trans, float* t_last, void* stream);
+int tir_composite_bwd(const float* sigma, const float* dist, const int64_t* offsets, int64_t n_rays,
+                      float distance_scale, const float* weight, const float* trans, const float* g_weight,
+                      float* g_sigma, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TENSOIR_B200_H */

@@ -1,0 +1,148 @@
+"""ctypes binding of the C ABI declared in include/tensoir_b200.h.
+
+The product path has NO fallback: if the shared library is missing or the tensors are not on a
+CUDA device, calls raise.  Build the library with ``python -c "import __graft_entry__ as g; g.build()"``
+(or ``python -m tensoir_b200.build``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libtensoir_b200.so")
+
+ABI_VERSION = 1
+CNT_MASK, CNT_DENSITY, CNT_APP, CNT_RAYS, CNT_OVERFLOW, CNT_SLOTS = 0, 1, 2, 3, 4, 8
+SAMPLE_STEP, SAMPLE_TABLE = 0, 1
+
+f32p = C.c_void_p
+
+
+class TirField(C.Structure):
+    _fields_ = [
+        ("dplane", C.c_void_p * 3), ("dline", C.c_void_p * 3), ("aplane", C.c_void_p * 3), ("aline", C.c_void_p * 3),
+        ("dC", C.c_int32), ("aC", C.c_int32), ("grid", C.c_int32 * 3),
+        ("aabb_lo", C.c_float * 3), ("aabb_hi", C.c_float * 3), ("inv_aabb", C.c_float * 3),
+        ("amask", C.c_void_p), ("acell", C.c_void_p), ("agrid", C.c_int32 * 3),
+        ("a_lo", C.c_float * 3), ("a_inv", C.c_float * 3),
+        ("density_shift", C.c_float), ("distance_scale", C.c_float), ("weight_thres", C.c_float),
+        ("softplus", C.c_int32),
+    ]
+
+
+class TirMlp(C.Structure):
+    _fields_ = [
+        ("w0", C.c_void_p), ("b0", C.c_void_p), ("w1", C.c_void_p), ("b1", C.c_void_p),
+        ("w2", C.c_void_p), ("b2", C.c_void_p), ("basis", C.c_void_p), ("light_line", C.c_void_p),
+        ("n_lights", C.c_int32), ("feat_dim", C.c_int32), ("hidden", C.c_int32), ("out_dim", C.c_int32),
+        ("pe_feat", C.c_int32), ("pe_x", C.c_int32),
+    ]
+
+
+class TirMarchCfg(C.Structure):
+    _fields_ = [
+        ("sampling", C.c_int32), ("n_samples", C.c_int32), ("step", C.c_float), ("near", C.c_float),
+        ("far", C.c_float), ("z_table", C.c_void_p), ("jitter", C.c_void_p), ("flags", C.c_int32),
+    ]
+
+
+MARCH_NO_BBOX = 1
+
+
+APP_SAMPLE_BYTES = 24  # sizeof(TirAppSample)
+
+EXPORTS = {
+    "tir_abi_version": (C.c_int, []),
+    "tir_pack_channels_last": (C.c_int, [f32p, f32p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "tir_unpack_channels_last_add": (C.c_int, [f32p, f32p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "tir_pack_alpha_mask": (C.c_int, [f32p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "tir_density_points": (C.c_int, [C.POINTER(TirField), f32p, C.c_int64, f32p, f32p, C.c_void_p]),
+    "tir_alpha_mask_points": (C.c_int, [C.POINTER(TirField), f32p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "tir_march_density": (C.c_int, [C.POINTER(TirField), f32p, f32p, C.c_int64, C.POINTER(TirMarchCfg),
+                                    f32p, f32p, f32p, C.c_void_p, C.c_void_p]),
+    "tir_march_radiance": (C.c_int, [C.POINTER(TirField), C.POINTER(TirMlp), f32p, f32p, C.c_void_p, C.c_int64,
+                                     C.POINTER(TirMarchCfg), f32p, f32p, f32p, f32p, C.c_void_p, C.c_void_p,
+                                     C.c_int64, C.c_void_p, C.c_void_p]),
+    "tir_secondary_radiance": (C.c_int, [C.POINTER(TirField), C.POINTER(TirMlp), f32p, f32p, C.c_void_p, C.c_int64,
+                                         f32p, C.c_int32, C.POINTER(TirMarchCfg), f32p, f32p, C.c_void_p,
+                                         C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "tir_app_mlp": (C.c_int, [C.POINTER(TirField), C.POINTER(TirMlp), C.c_void_p, C.c_void_p, C.c_int64, f32p,
+                              C.c_int32, C.c_void_p, f32p, C.c_void_p]),
+    "tir_app_mlp_points": (C.c_int, [C.POINTER(TirField), C.POINTER(TirMlp), f32p, f32p, C.c_void_p, C.c_int64,
+                                     C.c_int32, f32p, C.c_void_p]),
+    "tir_vm_app_products": (C.c_int, [C.POINTER(TirField), f32p, C.c_int64, f32p, C.c_void_p]),
+    "tir_vm_app_products_bwd": (C.c_int, [C.POINTER(TirField), f32p, C.c_int64, f32p, C.POINTER(C.c_void_p),
+                                          C.POINTER(C.c_void_p), C.c_void_p]),
+    "tir_vm_density_bwd": (C.c_int, [C.POINTER(TirField), f32p, C.c_int64, f32p, C.POINTER(C.c_void_p),
+                                     C.POINTER(C.c_void_p), C.c_void_p]),
+    "tir_vm_density_grad": (C.c_int, [C.POINTER(TirField), f32p, C.c_int64, f32p, f32p, C.c_void_p]),
+    "tir_vm_density_grad_bwd": (C.c_int, [C.POINTER(TirField), f32p, C.c_int64, f32p, f32p, C.POINTER(C.c_void_p),
+                                          C.POINTER(C.c_void_p), C.c_void_p]),
+    "tir_valid_samples_count": (C.c_int, [C.POINTER(TirField), f32p, f32p, C.c_int64, C.POINTER(TirMarchCfg),
+                                          C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tir_valid_samples_fill": (C.c_int, [C.POINTER(TirField), f32p, f32p, C.c_int64, C.POINTER(TirMarchCfg),
+                                         C.c_void_p, C.c_void_p, C.c_void_p, f32p, f32p, f32p, C.c_void_p]),
+    "tir_composite_fwd": (C.c_int, [f32p, f32p, C.c_void_p, C.c_int64, C.c_float, f32p, f32p, f32p, C.c_void_p]),
+    "tir_composite_bwd": (C.c_int, [f32p, f32p, C.c_void_p, C.c_int64, C.c_float, f32p, f32p, f32p, f32p,
+                                    C.c_void_p]),
+}
+
+_lib = None
+
+
+class TirError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library once; raise loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TirError(f"{LIB_PATH} not found: the CUDA extension is not built. Run "
+                       f"`python -c 'import __graft_entry__ as g; g.build()'` from the repo root. "
+                       f"tensoir_b200 has no CPU / PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in EXPORTS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    v = lib.tir_abi_version()
+    if v != ABI_VERSION:
+        raise TirError(f"ABI version mismatch: library {v}, binding {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+_STATUS = {-1: "TIR_ERR_NULL", -2: "TIR_ERR_SHAPE", -3: "TIR_ERR_CONFIG", -4: "TIR_ERR_CAPACITY"}
+
+
+def check(rc, what):
+    if rc == 0:
+        return
+    if rc < 0:
+        raise TirError(f"{what}: {_STATUS.get(rc, rc)}")
+    raise TirError(f"{what}: cudaError {rc}")
+
+
+def dptr(t, dtype=torch.float32, allow_none=False):
+    """Device pointer of a contiguous CUDA tensor (the ABI takes raw device pointers)."""
+    if t is None:
+        if allow_none:
+            return None
+        raise TirError("required tensor is None")
+    if not t.is_cuda:
+        raise TirError("tensoir_b200 kernels need CUDA tensors (no CPU fallback)")
+    if dtype is not None and t.dtype != dtype:
+        raise TirError(f"expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise TirError("tensor must be contiguous")
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,270 @@
+// Fused ray march: sample generation -> bbox / alpha-mask filter -> VM density gather -> softplus ->
+// alpha -> transmittance scan -> compositing (+ compaction of the samples that need appearance).
+//
+// Mapping: one warp per ray, lanes = consecutive samples along the ray.  Valid samples (in bbox and
+// alpha-mask > 0) are compacted into a per-warp shared-memory queue and the expensive gather runs on
+// full 32-lane batches; invalid samples have sigma = 0 => alpha = 0 => T factor (1 - 0 + 1e-10) == 1.0f
+// in fp32, so dropping them is exact (raw2alpha, tensorBase:21-28).
+#include "tir_device.cuh"
+
+using namespace tir;
+
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kQueue = 64;
+
+struct QEntry {
+  float x, y, z;   // normalised coords
+  int s;           // sample index along the ray
+};
+
+struct MarchParams {
+  TirField f;
+  TirMarchCfg cfg;
+  // explicit rays
+  const float* rays_o;
+  const float* rays_d;
+  // dense secondary generation
+  const float* surf_xyz;
+  const float* normals;
+  const float* dirs;
+  int n_dirs;
+  int64_t n_rays;
+  float* t_last;
+  float* acc;
+  float* depth;
+  TirAppSample* samples;
+  uint32_t* sample_count;
+  int64_t capacity;
+  unsigned long long* counters;
+};
+
+template <int C, int SAMPLING, bool WITH_APP, bool DENSE>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) march_kernel(const MarchParams p) {
+  __shared__ QEntry queue[kWarpsPerBlock][kQueue];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  QEntry* q = queue[warp];
+  const TirField& f = p.f;
+  const int N = p.cfg.n_samples;
+  const float scale = f.distance_scale;
+  unsigned long long c_mask = 0, c_density = 0, c_app = 0, c_rays = 0, c_over = 0;
+
+  const int64_t warp_stride = (int64_t)gridDim.x * kWarpsPerBlock;
+  for (int64_t ray = (int64_t)blockIdx.x * kWarpsPerBlock + warp; ray < p.n_rays; ray += warp_stride) {
+    float ox, oy, oz, dx, dy, dz;
+    if (DENSE) {
+      const int64_t pt = ray / p.n_dirs;
+      const int di = (int)(ray - pt * p.n_dirs);
+      dx = __ldg(p.dirs + di * 3 + 0); dy = __ldg(p.dirs + di * 3 + 1); dz = __ldg(p.dirs + di * 3 + 2);
+      const float nx = __ldg(p.normals + pt * 3 + 0), ny = __ldg(p.normals + pt * 3 + 1),
+                  nz = __ldg(p.normals + pt * 3 + 2);
+      // cosine = clamp(einsum(surf2l, normal), 0) > 1e-6 (relight_utils.py:433-435)
+      const float cosine = fmaxf(fmaf(dz, nz, fmaf(dy, ny, __fmul_rn(dx, nx))), 0.f);
+      if (!(cosine > 1e-6f)) continue;
+      ox = __ldg(p.surf_xyz + pt * 3 + 0); oy = __ldg(p.surf_xyz + pt * 3 + 1); oz = __ldg(p.surf_xyz + pt * 3 + 2);
+    } else {
+      ox = __ldg(p.rays_o + ray * 3 + 0); oy = __ldg(p.rays_o + ray * 3 + 1); oz = __ldg(p.rays_o + ray * 3 + 2);
+      dx = __ldg(p.rays_d + ray * 3 + 0); dy = __ldg(p.rays_d + ray * 3 + 1); dz = __ldg(p.rays_d + ray * 3 + 2);
+    }
+    c_rays += (lane == 0);
+
+    float tmin = 0.f, jit = 0.f;
+    if (SAMPLING == TIR_SAMPLE_STEP) {
+      // sample_ray (tensorBase:705-724)
+      const float vx = dx == 0.f ? 1e-6f : dx, vy = dy == 0.f ? 1e-6f : dy, vz = dz == 0.f ? 1e-6f : dz;
+      const float ax = __fdiv_rn(__fsub_rn(f.aabb_hi[0], ox), vx), bx = __fdiv_rn(__fsub_rn(f.aabb_lo[0], ox), vx);
+      const float ay = __fdiv_rn(__fsub_rn(f.aabb_hi[1], oy), vy), by = __fdiv_rn(__fsub_rn(f.aabb_lo[1], oy), vy);
+      const float az = __fdiv_rn(__fsub_rn(f.aabb_hi[2], oz), vz), bz = __fdiv_rn(__fsub_rn(f.aabb_lo[2], oz), vz);
+      tmin = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+      tmin = fminf(fmaxf(tmin, p.cfg.near), p.cfg.far);
+      jit = p.cfg.jitter ? __ldg(p.cfg.jitter + ray) : 0.f;
+    }
+    auto z_of = [&](int s) -> float {
+      if (SAMPLING == TIR_SAMPLE_STEP) return __fadd_rn(tmin, __fmul_rn(p.cfg.step, __fadd_rn((float)s, jit)));
+      return __ldg(p.cfg.z_table + s);
+    };
+
+    float carry = 1.f, acc = 0.f, dep = 0.f;
+    int qn = 0;
+
+    // gather + composite the first `nb` queue entries (nb <= 32), in ray order
+    auto process = [&](int nb) {
+      float sigma = 0.f, zs = 0.f, dist = 0.f;
+      QEntry e = q[lane < nb ? lane : 0];
+      const bool active = lane < nb;
+      if (active) {
+        sigma = feature_to_sigma(f, density_feature<C>(f, e.x, e.y, e.z));
+        zs = z_of(e.s);
+        dist = (e.s + 1 < N) ? __fsub_rn(z_of(e.s + 1), zs) : 0.f;
+      }
+      // raw2alpha: alpha = 1 - exp(-sigma * (dist*scale)); T = cumprod(1 - alpha + 1e-10)
+      const float alpha = active ? __fsub_rn(1.f, expf(__fmul_rn(-sigma, __fmul_rn(dist, scale)))) : 0.f;
+      float incl = __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        float up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl = __fmul_rn(incl, up);
+      }
+      float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+      excl = __fmul_rn(carry, lane ? excl : 1.f);
+      const float w = __fmul_rn(alpha, excl);
+      acc += w;
+      dep = fmaf(w, zs, dep);
+      carry = __fmul_rn(carry, __shfl_sync(0xffffffffu, incl, 31));
+      if (WITH_APP) {
+        const bool app = active && (w > f.weight_thres);
+        const unsigned m = __ballot_sync(0xffffffffu, app);
+        if (m) {
+          unsigned base = 0;
+          const int cnt = __popc(m);
+          if (lane == 0) base = atomicAdd(p.sample_count, (unsigned)cnt);
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (app) {
+            const unsigned slot = base + __popc(m & ((1u << lane) - 1u));
+            if ((int64_t)slot < p.capacity) {
+              TirAppSample sm;
+              sm.xn[0] = e.x; sm.xn[1] = e.y; sm.xn[2] = e.z; sm.weight = w; sm.ray = (int)ray; sm.sample = e.s;
+              p.samples[slot] = sm;
+              c_app += 1;
+            } else {
+              c_over += 1;
+            }
+          }
+        }
+      } else {
+        c_app += (active && (w > f.weight_thres));
+      }
+      c_density += active;
+    };
+
+    for (int base = 0; base < N; base += 32) {
+      const int s = base + lane;
+      bool valid = false;
+      float nx = 0.f, ny = 0.f, nz = 0.f;
+      if (s < N) {
+        const float z = z_of(s);
+        const float px = __fadd_rn(ox, __fmul_rn(dx, z)), py = __fadd_rn(oy, __fmul_rn(dy, z)),
+                    pz = __fadd_rn(oz, __fmul_rn(dz, z));
+        const bool out = (f.aabb_lo[0] > px) | (px > f.aabb_hi[0]) | (f.aabb_lo[1] > py) | (py > f.aabb_hi[1]) |
+                         (f.aabb_lo[2] > pz) | (pz > f.aabb_hi[2]);
+        if (!out) {
+          valid = true;
+          if (f.amask) {
+            c_mask += 1;
+            valid = alpha_mask_positive(f, px, py, pz);
+          }
+          // normalize_coord (tensorBase:640-641)
+          nx = __fsub_rn(__fmul_rn(__fsub_rn(px, f.aabb_lo[0]), f.inv_aabb[0]), 1.f);
+          ny = __fsub_rn(__fmul_rn(__fsub_rn(py, f.aabb_lo[1]), f.inv_aabb[1]), 1.f);
+          nz = __fsub_rn(__fmul_rn(__fsub_rn(pz, f.aabb_lo[2]), f.inv_aabb[2]), 1.f);
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, valid);
+      if (valid) {
+        QEntry e; e.x = nx; e.y = ny; e.z = nz; e.s = s;
+        q[qn + __popc(m & ((1u << lane) - 1u))] = e;
+      }
+      qn += __popc(m);
+      __syncwarp();
+      if (qn >= 32) {
+        process(32);
+        __syncwarp();
+        const int rest = qn - 32;
+        QEntry mv;
+        if (lane < rest) mv = q[32 + lane];
+        __syncwarp();
+        if (lane < rest) q[lane] = mv;
+        qn = rest;
+        __syncwarp();
+      }
+    }
+    if (qn > 0) process(qn);
+    __syncwarp();
+
+    acc = warp_sum(acc);
+    dep = warp_sum(dep);
+    if (lane == 0) {
+      if (p.t_last) p.t_last[ray] = carry;
+      if (p.acc) p.acc[ray] = acc;
+      if (p.depth) p.depth[ray] = dep;
+    }
+  }
+
+  c_mask = warp_sum_u64(c_mask); c_density = warp_sum_u64(c_density); c_app = warp_sum_u64(c_app);
+  c_rays = warp_sum_u64(c_rays); c_over = warp_sum_u64(c_over);
+  if (lane == 0 && p.counters) {
+    if (c_mask) atomicAdd(p.counters + TIR_CNT_MASK, c_mask);
+    if (c_density) atomicAdd(p.counters + TIR_CNT_DENSITY, c_density);
+    if (c_app) atomicAdd(p.counters + TIR_CNT_APP, c_app);
+    if (c_rays) atomicAdd(p.counters + TIR_CNT_RAYS, c_rays);
+    if (c_over) atomicAdd(p.counters + TIR_CNT_OVERFLOW, c_over);
+  }
+}
+
+template <bool WITH_APP, bool DENSE>
+int launch_march(const MarchParams& p, cudaStream_t stream) {
+  if (p.n_rays <= 0) return TIR_OK;
+  if (p.f.dC != 16) return TIR_ERR_SHAPE;
+  if (p.cfg.n_samples <= 0) return TIR_ERR_CONFIG;
+  int64_t blocks = (p.n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  const int64_t max_blocks = 148 * 8;   // persistent: 8 CTAs x 8 warps per SM
+  if (blocks > max_blocks) blocks = max_blocks;
+  if (p.cfg.sampling == TIR_SAMPLE_STEP) {
+    march_kernel<16, TIR_SAMPLE_STEP, WITH_APP, DENSE><<<(int)blocks, kWarpsPerBlock * 32, 0, stream>>>(p);
+  } else if (p.cfg.sampling == TIR_SAMPLE_TABLE) {
+    if (!p.cfg.z_table) return TIR_ERR_NULL;
+    march_kernel<16, TIR_SAMPLE_TABLE, WITH_APP, DENSE><<<(int)blocks, kWarpsPerBlock * 32, 0, stream>>>(p);
+  } else {
+    return TIR_ERR_CONFIG;
+  }
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" int tir_march_density(const TirField* field, const float* rays_o, const float* rays_d, int64_t n_rays,
+                                 const TirMarchCfg* cfg, float* t_last, float* acc, float* depth,
+                                 uint64_t* counters, void* stream) {
+  if (!field || !cfg || !rays_o || !rays_d) return TIR_ERR_NULL;
+  MarchParams p{};
+  p.f = *field; p.cfg = *cfg; p.rays_o = rays_o; p.rays_d = rays_d; p.n_rays = n_rays;
+  p.t_last = t_last; p.acc = acc; p.depth = depth; p.counters = (unsigned long long*)counters;
+  return launch_march<false, false>(p, (cudaStream_t)stream);
+}
+
+extern "C" int tir_march_radiance(const TirField* field, const TirMlp* mlp, const float* rays_o, const float* rays_d,
+                                  const int32_t* light_idx, int64_t n_rays, const TirMarchCfg* cfg,
+                                  float* t_last, float* acc, float* depth, float* rgb,
+                                  TirAppSample* samples, uint32_t* sample_count, int64_t capacity,
+                                  uint64_t* counters, void* stream) {
+  if (!field || !mlp || !cfg || !rays_o || !rays_d || !rgb || !samples || !sample_count) return TIR_ERR_NULL;
+  if (capacity <= 0) return TIR_ERR_CAPACITY;
+  MarchParams p{};
+  p.f = *field; p.cfg = *cfg; p.rays_o = rays_o; p.rays_d = rays_d; p.n_rays = n_rays;
+  p.t_last = t_last; p.acc = acc; p.depth = depth; p.counters = (unsigned long long*)counters;
+  p.samples = samples; p.sample_count = sample_count; p.capacity = capacity;
+  int rc = launch_march<true, false>(p, (cudaStream_t)stream);
+  if (rc) return rc;
+  return tir_app_mlp(field, mlp, samples, sample_count, capacity, rays_d, 0, light_idx, rgb, stream);
+}
+
+extern "C" int tir_secondary_radiance(const TirField* field, const TirMlp* mlp, const float* surf_xyz,
+                                      const float* normals, const int32_t* light_idx, int64_t n_pts,
+                                      const float* dirs, int32_t n_dirs, const TirMarchCfg* cfg, float* vis,
+                                      float* indirect, TirAppSample* samples, uint32_t* sample_count,
+                                      int64_t capacity, uint64_t* counters, void* stream) {
+  if (!field || !mlp || !cfg || !surf_xyz || !normals || !dirs || !vis || !indirect || !samples || !sample_count)
+    return TIR_ERR_NULL;
+  if (n_dirs <= 0) return TIR_ERR_SHAPE;
+  if (capacity <= 0) return TIR_ERR_CAPACITY;
+  MarchParams p{};
+  p.f = *field; p.cfg = *cfg; p.surf_xyz = surf_xyz; p.normals = normals; p.dirs = dirs; p.n_dirs = n_dirs;
+  p.n_rays = n_pts * (int64_t)n_dirs;
+  p.t_last = vis; p.counters = (unsigned long long*)counters;
+  p.samples = samples; p.sample_count = sample_count; p.capacity = capacity;
+  int rc = launch_march<true, true>(p, (cudaStream_t)stream);
+  if (rc) return rc;
+  return tir_app_mlp(field, mlp, samples, sample_count, capacity, dirs, n_dirs, light_idx, indirect, stream);
+}

@@ -1,0 +1,121 @@
+// Layout shadows + point-wise field queries.
+#include "tir_device.cuh"
+
+using namespace tir;
+
+extern "C" int tir_abi_version(void) { return TIR_ABI_VERSION; }
+
+// [C][H*W] -> [H*W][C] through a padded shared tile so both sides are coalesced.
+__global__ void pack_channels_last_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int HW) {
+  __shared__ float tile[32][33];
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int c = c0 + r, p = p0 + threadIdx.x;
+    tile[r][threadIdx.x] = (c < C && p < HW) ? in[(size_t)c * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int p = p0 + r, c = c0 + threadIdx.x;
+    if (p < HW && c < C) out[(size_t)p * C + c] = tile[threadIdx.x][r];
+  }
+}
+
+__global__ void unpack_channels_last_add_kernel(const float* __restrict__ cl, float* __restrict__ nchw, int C, int HW) {
+  __shared__ float tile[32][33];
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int p = p0 + r, c = c0 + threadIdx.x;
+    tile[r][threadIdx.x] = (p < HW && c < C) ? cl[(size_t)p * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int c = c0 + r, p = p0 + threadIdx.x;
+    if (c < C && p < HW) nchw[(size_t)c * HW + p] += tile[threadIdx.x][r];
+  }
+}
+
+extern "C" int tir_pack_channels_last(const float* nchw, float* out, int32_t C, int32_t H, int32_t W, void* stream) {
+  if (!nchw || !out) return TIR_ERR_NULL;
+  if (C <= 0 || H <= 0 || W <= 0) return TIR_ERR_SHAPE;
+  const int HW = H * W;
+  dim3 grid((HW + 31) / 32, (C + 31) / 32), block(32, 8);
+  pack_channels_last_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(nchw, out, C, HW);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int tir_unpack_channels_last_add(const float* cl, float* nchw, int32_t C, int32_t H, int32_t W, void* stream) {
+  if (!nchw || !cl) return TIR_ERR_NULL;
+  if (C <= 0 || H <= 0 || W <= 0) return TIR_ERR_SHAPE;
+  const int HW = H * W;
+  dim3 grid((HW + 31) / 32, (C + 31) / 32), block(32, 8);
+  unpack_channels_last_add_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(cl, nchw, C, HW);
+  return (int)cudaGetLastError();
+}
+
+__global__ void pack_alpha_kernel(const float* __restrict__ vol, uint8_t* __restrict__ corners,
+                                  uint8_t* __restrict__ cells, int X, int Y, int Z, int pass) {
+  size_t n = (size_t)X * Y * Z;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    if (pass == 0) {
+      corners[i] = vol[i] > 0.f ? 1 : 0;
+    } else {
+      int x = (int)(i % X), y = (int)((i / X) % Y), z = (int)(i / ((size_t)X * Y));
+      uint8_t any = 0;
+      for (int dz = 0; dz < 2; ++dz)
+        for (int dy = 0; dy < 2; ++dy)
+          for (int dx = 0; dx < 2; ++dx) {
+            int xx = x + dx, yy = y + dy, zz = z + dz;
+            if (xx < X && yy < Y && zz < Z) any |= corners[((size_t)zz * Y + yy) * X + xx];
+          }
+      cells[i] = any;
+    }
+  }
+}
+
+extern "C" int tir_pack_alpha_mask(const float* volume, uint8_t* corners, uint8_t* cells,
+                                   int32_t X, int32_t Y, int32_t Z, void* stream) {
+  if (!volume || !corners || !cells) return TIR_ERR_NULL;
+  if (X <= 0 || Y <= 0 || Z <= 0) return TIR_ERR_SHAPE;
+  size_t n = (size_t)X * Y * Z;
+  int blocks = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+  pack_alpha_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(volume, corners, cells, X, Y, Z, 0);
+  pack_alpha_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(volume, corners, cells, X, Y, Z, 1);
+  return (int)cudaGetLastError();
+}
+
+template <int C>
+__global__ void density_points_kernel(TirField f, const float* __restrict__ xn, int64_t n,
+                                      float* __restrict__ feature, float* __restrict__ sigma) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float ft = density_feature<C>(f, xn[i * 3 + 0], xn[i * 3 + 1], xn[i * 3 + 2]);
+    if (feature) feature[i] = ft;
+    if (sigma) sigma[i] = feature_to_sigma(f, ft);
+  }
+}
+
+extern "C" int tir_density_points(const TirField* field, const float* xn, int64_t n, float* feature, float* sigma,
+                                  void* stream) {
+  if (!field || !xn) return TIR_ERR_NULL;
+  if (n <= 0) return TIR_OK;
+  int blocks = (int)((n + 127) / 128 < 148 * 16 ? (n + 127) / 128 : 148 * 16);
+  if (field->dC == 16)
+    density_points_kernel<16><<<blocks, 128, 0, (cudaStream_t)stream>>>(*field, xn, n, feature, sigma);
+  else if (field->dC == 8)
+    density_points_kernel<8><<<blocks, 128, 0, (cudaStream_t)stream>>>(*field, xn, n, feature, sigma);
+  else
+    return TIR_ERR_SHAPE;
+  return (int)cudaGetLastError();
+}
+
+__global__ void alpha_points_kernel(TirField f, const float* __restrict__ xyz, int64_t n, uint8_t* __restrict__ mask) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    mask[i] = alpha_mask_positive(f, xyz[i * 3 + 0], xyz[i * 3 + 1], xyz[i * 3 + 2]) ? 1 : 0;
+}
+
+extern "C" int tir_alpha_mask_points(const TirField* field, const float* xyz, int64_t n, uint8_t* mask, void* stream) {
+  if (!field || !xyz || !mask || !field->amask || !field->acell) return TIR_ERR_NULL;
+  if (n <= 0) return TIR_OK;
+  int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  alpha_points_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*field, xyz, n, mask);
+  return (int)cudaGetLastError();
+}

@@ -1,0 +1,126 @@
+"""Device-side view of a TensorVMSplit: channel-last shadows of the VM factors, the packed alpha
+mask and the POD structs of include/tensoir_b200.h.
+
+PyTorch keeps owning the parameters in the reference NCHW layout (state_dict compatible); the
+kernels read shadows that are rebuilt whenever a parameter's (data_ptr, version, shape) changes —
+i.e. after every optimizer step and after shrink / upsample_volume_grid rebinding
+(tensoRF_rotated_lights.py:226-288).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+
+def _key(ts):
+    return tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in ts)
+
+
+class DeviceField:
+    def __init__(self):
+        self._vm_key = None
+        self._mask_key = None
+        self.dplane = self.dline = self.aplane = self.aline = None
+        self.amask = self.acell = None
+        self.struct = _lib.TirField()
+        self._keep = []
+
+    # ---- VM factors -------------------------------------------------------------------
+    def _pack(self, lib, p):
+        _, Cc, H, W = p.shape
+        src = p.detach().contiguous()
+        out = torch.empty((H, W, Cc), device=p.device, dtype=torch.float32)
+        _lib.check(lib.tir_pack_channels_last(_lib.dptr(src), _lib.dptr(out), Cc, H, W, _lib.stream_ptr()), "pack")
+        return out
+
+    def refresh(self, model) -> "_lib.TirField":
+        """Bring shadows + struct up to date with ``model`` (a TensorVMSplit-like module)."""
+        lib = _lib.load()
+        params = list(model.density_plane) + list(model.density_line) + list(model.app_plane) + list(model.app_line)
+        key = _key(params)
+        s = self.struct
+        if key != self._vm_key:
+            self.dplane = [self._pack(lib, p) for p in model.density_plane]
+            self.dline = [self._pack(lib, p) for p in model.density_line]
+            self.aplane = [self._pack(lib, p) for p in model.app_plane]
+            self.aline = [self._pack(lib, p) for p in model.app_line]
+            for k in range(3):
+                s.dplane[k] = self.dplane[k].data_ptr()
+                s.dline[k] = self.dline[k].data_ptr()
+                s.aplane[k] = self.aplane[k].data_ptr()
+                s.aline[k] = self.aline[k].data_ptr()
+            dcs = {p.shape[1] for p in model.density_plane}
+            acs = {p.shape[1] for p in model.app_plane}
+            if len(dcs) != 1 or len(acs) != 1:
+                raise _lib.TirError("kernels need equal channel counts across the three orientations")
+            s.dC, s.aC = dcs.pop(), acs.pop()
+            self._vm_key = key
+        gs = [int(g) for g in model.gridSize.tolist()]
+        lo, hi = model.aabb[0].tolist(), model.aabb[1].tolist()
+        inv = model.invaabbSize.tolist()
+        for i in range(3):
+            s.grid[i] = gs[i]
+            s.aabb_lo[i], s.aabb_hi[i], s.inv_aabb[i] = lo[i], hi[i], inv[i]
+        am = getattr(model, "alphaMask", None)
+        if am is None:
+            s.amask = None
+            s.acell = None
+            self._mask_key = None
+        else:
+            vol = am.alpha_volume
+            mkey = _key([vol])
+            if mkey != self._mask_key:
+                Z, Y, X = vol.shape[-3:]
+                v = vol.detach().reshape(Z, Y, X).contiguous().float()
+                self.amask = torch.empty((Z, Y, X), device=v.device, dtype=torch.uint8)
+                self.acell = torch.empty((Z, Y, X), device=v.device, dtype=torch.uint8)
+                _lib.check(lib.tir_pack_alpha_mask(_lib.dptr(v), _lib.dptr(self.amask, torch.uint8),
+                                                   _lib.dptr(self.acell, torch.uint8), X, Y, Z, _lib.stream_ptr()),
+                           "pack_alpha_mask")
+                self._mask_key = mkey
+            Z, Y, X = vol.shape[-3:]
+            s.amask, s.acell = self.amask.data_ptr(), self.acell.data_ptr()
+            s.agrid[0], s.agrid[1], s.agrid[2] = X, Y, Z
+            alo, ainv = am.aabb[0].tolist(), am.invgridSize.tolist()
+            for i in range(3):
+                s.a_lo[i], s.a_inv[i] = alo[i], ainv[i]
+        s.density_shift = float(model.density_shift)
+        s.distance_scale = float(model.distance_scale)
+        s.weight_thres = float(model.rayMarch_weight_thres)
+        s.softplus = 1 if model.fea2denseAct == "softplus" else 0
+        return s
+
+
+def mlp_struct(model, head: str, keep: list, light: str = "index") -> "_lib.TirMlp":
+    """TirMlp for one head of ``model``: 'renderModule' | 'renderModule_brdf' | 'renderModule_normal'.
+    light: 'index' (light_line[light_idx]), 'mean' (mean over lights, compute_intrinfeature) or 'none'."""
+    mod = getattr(model, head)
+    m = _lib.TirMlp()
+    ts = [mod.mlp[0].weight, mod.mlp[0].bias, mod.mlp[2].weight, mod.mlp[2].bias, mod.mlp[4].weight,
+          mod.mlp[4].bias, model.basis_mat.weight]
+    ts = [t.detach().contiguous() for t in ts]
+    keep.extend(ts)
+    m.w0, m.b0, m.w1, m.b1, m.w2, m.b2, m.basis = [t.data_ptr() for t in ts]
+    ll = getattr(model, "light_line", None)
+    if ll is None or light == "none":
+        m.light_line, m.n_lights = None, 0
+    elif light == "mean":
+        # torch.mean(self.light_line(arange(light_num)), dim=0)  (tensoRF_rotated_lights.py:160-161)
+        idx = torch.arange(model.light_num, device=ll.weight.device, dtype=torch.int32)
+        row = torch.mean(ll(idx), dim=0).detach().contiguous().view(1, -1)
+        keep.append(row)
+        m.light_line, m.n_lights = row.data_ptr(), 1
+    else:
+        w = ll.weight.detach().contiguous()
+        keep.append(w)
+        m.light_line, m.n_lights = w.data_ptr(), w.shape[0]
+    m.feat_dim = int(model.app_dim)
+    m.hidden = int(mod.mlp[0].weight.shape[0])
+    m.out_dim = int(mod.mlp[4].weight.shape[0])
+    m.pe_feat = int(mod.feape)
+    m.pe_x = int(getattr(mod, "viewpe", getattr(mod, "pospe", 0)))
+    return m

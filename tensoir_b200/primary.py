@@ -1,0 +1,181 @@
+"""The primary march of TensorBase.forward (models/tensorBase_rotated_lights.py:868-1036) and
+TensorBase_Init.forward (models/tensorBase_init.py:406-462), restructured around compacted sample lists.
+
+The reference materialises [N_rays, N_samples, *] tensors and masks them; here the kernels emit the
+ray-sorted list of valid samples (2-5 % of N*S), the density gather / compositing / appearance gather run on
+that list with custom forward+backward kernels, and the per-ray maps are segment sums.  Row order of the
+lists equals the reference's boolean-mask order, so host-side random draws (jitter on the CPU, xyz noise on
+the device, background coin on the CPU) consume the generators exactly as the reference does.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from . import vm_autograd as vm
+
+
+def _linear2srgb(t):
+    from .relight_utils import linear2srgb_torch
+    return linear2srgb_torch(t)
+
+
+def _segment_sum(values, ray_id, n_rays):
+    """sum over the samples of each ray: torch.sum(weight[..., None] * x, -2) of the reference."""
+    if values.dim() == 1:
+        out = torch.zeros(n_rays, device=values.device, dtype=values.dtype)
+    else:
+        out = torch.zeros((n_rays, values.shape[1]), device=values.device, dtype=values.dtype)
+    return out.index_add_(0, ray_id, values)
+
+
+def any_sample_in_mask(model, rays_o, rays_d, n_samples):
+    """(alphaMask.sample_alpha(xyz_sampled) > 0).any(-1) of filtering_rays (tensorBase:803-804)."""
+    res = vm.valid_samples(model, rays_o, rays_d, n_samples=n_samples, no_bbox=True, count_only=True)
+    return res["counts"] > 0
+
+
+def _derived_normals(model, xn):
+    """compute_derived_normals (tensorBase:839-856): -normalize(d sigma / d x_hat), with
+    d sigma = softplus'(f + shift) * d f (analytic, kernel) instead of autograd.grad(create_graph=True)."""
+    feat, dfdx = vm.density_feature_and_grad(model, xn)
+    if model.fea2denseAct == "softplus":
+        x = feat + model.density_shift
+        dsig = torch.where(x > 20, torch.ones_like(x), torch.sigmoid(x))
+    else:
+        dsig = (feat > 0).to(feat.dtype)
+    grad = dsig[:, None] * dfdx
+    return -F.normalize(grad, p=2, dim=-1, eps=1e-6)
+
+
+def march(model, rays, is_train, n_samples, counters=None):
+    """Shared front half: valid list -> sigma -> weights.  Returns a dict."""
+    n_rays = rays.shape[0]
+    jitter = None
+    if is_train:
+        # the reference draws the per-ray jitter on the CPU (rand_like of a CPU tensor, tensorBase:714-718)
+        jitter = torch.rand(n_rays, 1).to(rays.device)
+    lst = vm.valid_samples(model, rays[:, :3], rays[:, 3:6], n_samples=n_samples, jitter=jitter, counters=counters)
+    ray_id = lst["ray"].long()
+    if lst["xn"].shape[0] > 0:
+        feat = vm.density_feature(model, lst["xn"])
+        sigma = model.feature2density(feat)
+    else:
+        sigma = torch.zeros(0, device=rays.device)
+    weight, t_last = vm.composite(sigma, lst["dist"], lst["offsets"], model.distance_scale)
+    lst.update(ray_id=ray_id, sigma=sigma, weight=weight, t_last=t_last)
+    return lst
+
+
+def forward_relight(model, rays_chunk, light_idx, white_bg=True, is_train=False, is_relight=True, N_samples=-1):
+    dev = rays_chunk.device
+    rays = rays_chunk.float()
+    n_rays = rays.shape[0]
+    viewdirs = rays[:, 3:6]
+    m = march(model, rays, is_train, N_samples, counters=model.__dict__.get("_tir_counters"))
+    ray_id, weight, xn = m["ray_id"], m["weight"], m["xn"]
+
+    app_idx = torch.nonzero(weight > model.rayMarch_weight_thres).reshape(-1)
+    n_app = app_idx.shape[0]
+    cnt = model.__dict__.get("_tir_counters")
+    if cnt is not None:
+        cnt[2] += n_app
+    w_a = weight[app_idx]
+    r_a = ray_id[app_idx]
+    x_a = xn[app_idx]
+
+    acc_map = _segment_sum(weight, ray_id, n_rays)
+    depth_map = _segment_sum(weight * m["z"], ray_id, n_rays)
+
+    z3 = torch.zeros(n_rays, 3, device=dev)
+    z1 = torch.zeros(n_rays, 1, device=dev)
+    rgb_map, normal_map, albedo_map = z3, z3.clone(), z3.clone()
+    roughness_map, nd_map, no_map, ac_map, rc_map = z1, z1.clone(), z1.clone(), z1.clone(), z1.clone()
+    if n_app > 0:
+        vd = viewdirs[r_a]
+        li = light_idx.reshape(-1)[r_a]
+        rad, intr = model.compute_bothfeature(x_a, li)
+        rgb = model.renderModule(x_a, vd, rad)
+        rgb_map = _segment_sum(w_a[:, None] * rgb, r_a, n_rays)
+        if is_relight:
+            brdf = model.renderModule_brdf(x_a, intr)
+            v_alb, v_rough = brdf[..., :3], (brdf[..., 3:4] * 0.9 + 0.09)
+            # device-side draw, same shape/order as torch.randn_like(xyz_sampled[app_mask]) (tensorBase:937)
+            draw = model.__dict__.get("_tir_randn_like")       # test hook: replay the oracle's CPU stream
+            x_j = x_a + (draw(x_a) if draw is not None else torch.randn_like(x_a)) * 0.01
+            brdf_j = model.renderModule_brdf(x_j, model.compute_intrinfeature(x_j))
+            a_cost = model.compute_relative_smoothness_loss(v_alb, brdf_j[..., :3])
+            r_cost = model.compute_relative_smoothness_loss(v_rough, brdf_j[..., 3:4] * 0.9 + 0.09)
+            if model.normals_kind == "purely_predicted":
+                v_n = model.renderModule_normal(x_a, intr)
+                nd = no = None
+            elif model.normals_kind == "purely_derived":
+                v_n = _derived_normals(model, x_a)
+                nd = no = None
+            else:  # derived_plus_predicted
+                d_n = _derived_normals(model, x_a)
+                v_n = model.renderModule_normal(x_a, intr)
+                nd = torch.sum(torch.pow(v_n - d_n, 2), dim=-1, keepdim=True)
+                no = torch.sum(vd * v_n, dim=-1, keepdim=True).clamp(min=0)
+            normal_map = _segment_sum(w_a[:, None] * v_n, r_a, n_rays)
+            albedo_map = _segment_sum(w_a[:, None] * v_alb, r_a, n_rays)
+            roughness_map = _segment_sum(w_a[:, None] * v_rough, r_a, n_rays)
+            ac_map = _segment_sum(w_a[:, None] * a_cost, r_a, n_rays)
+            rc_map = _segment_sum(w_a[:, None] * r_cost, r_a, n_rays)
+            if nd is not None:
+                nd_map = _segment_sum(w_a[:, None] * nd, r_a, n_rays)
+                no_map = _segment_sum(w_a[:, None] * no, r_a, n_rays)
+
+    def bg():
+        # white_bg short-circuits the CPU coin (tensorBase:979 / :1004)
+        return white_bg or (is_train and bool(torch.rand((1,)) < 0.5))
+
+    if not is_relight:
+        if bg():
+            depth_map = depth_map + (1. - acc_map) * rays[..., -1]
+            rgb_map = rgb_map + (1. - acc_map[..., None])
+        return rgb_map, depth_map, None, None, None, None, acc_map, None, None, None, None, None
+
+    fresnel_map = torch.zeros_like(albedo_map).fill_(model.fixed_fresnel)
+    albedo_smoothness_loss = torch.mean(ac_map)
+    roughness_smoothness_loss = torch.mean(rc_map)
+    if bg():
+        depth_map = depth_map + (1. - acc_map) * rays[..., -1]
+        rgb_map = rgb_map + (1. - acc_map[..., None])
+        normal_map = normal_map + (1 - acc_map[..., None]) * torch.tensor([0.0, 0.0, 1.0], device=dev)
+        albedo_map = albedo_map + (1 - acc_map[..., None])
+        roughness_map = roughness_map + (1 - acc_map[..., None])
+        fresnel_map = fresnel_map + (1 - acc_map[..., None])
+    rgb_map = rgb_map.clamp(0, 1)
+    if rgb_map.shape[0] > 0:
+        rgb_map = _linear2srgb(rgb_map)
+    albedo_map = albedo_map.clamp(0, 1)
+    fresnel_map = fresnel_map.clamp(0, 1)
+    roughness_map = roughness_map.clamp(0, 1)
+    normal_map = F.normalize(normal_map, p=2, dim=-1, eps=1e-6)
+    acc_mask = acc_map > 0.5
+    return (rgb_map, depth_map, normal_map, albedo_map, roughness_map, fresnel_map, acc_map, nd_map, no_map,
+            acc_mask, albedo_smoothness_loss, roughness_smoothness_loss)
+
+
+def forward_init(model, rays_chunk, white_bg=True, is_train=False, N_samples=-1):
+    """TensorBase_Init.forward (tensorBase_init.py:406-462) -> (rgb_map, depth_map)."""
+    rays = rays_chunk.float()
+    n_rays = rays.shape[0]
+    m = march(model, rays, is_train, N_samples, counters=model.__dict__.get("_tir_counters"))
+    ray_id, weight, xn = m["ray_id"], m["weight"], m["xn"]
+    app_idx = torch.nonzero(weight > model.rayMarch_weight_thres).reshape(-1)
+    acc_map = _segment_sum(weight, ray_id, n_rays)
+    rgb_map = torch.zeros(n_rays, 3, device=rays.device)
+    if app_idx.shape[0] > 0:
+        r_a = ray_id[app_idx]
+        feats = model.compute_appfeature(xn[app_idx])
+        rgb = model.renderModule(xn[app_idx], rays[:, 3:6][r_a], feats)
+        rgb_map = _segment_sum(weight[app_idx][:, None] * rgb, r_a, n_rays)
+    if white_bg or (is_train and bool(torch.rand((1,)) < 0.5)):
+        rgb_map = rgb_map + (1. - acc_map[..., None])
+    rgb_map = rgb_map.clamp(0, 1)
+    with torch.no_grad():
+        depth_map = _segment_sum(weight * m["z"], ray_id, n_rays)
+        depth_map = depth_map + (1. - acc_map) * rays[..., -1]
+    return rgb_map, depth_map

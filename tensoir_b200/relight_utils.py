@@ -1,0 +1,118 @@
+"""Host-side mirror of models/relight_utils.py: the physically-based shading integral.
+
+Secondary visibility / indirect-light rays — ~99 % of the work of a relight step —
+run in the fused CUDA march (csrc/tir_march.cu + csrc/tir_mlp.cu), generated on chip from
+(surface point, direction) pairs; the small differentiable epilogue (GGX, SG lights, quadrature, sRGB)
+stays in PyTorch so autograd reaches normal / albedo / roughness / lgtSGs exactly as in the reference
+(the secondary march is @torch.no_grad in the reference too, relight_utils.py:344, :777).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import ops
+
+
+def safe_l2_normalize(x, dim=None, eps=1e-6):
+    return F.normalize(x, p=2, dim=dim, eps=eps)
+
+
+def GGX_specular(normal, pts2c, pts2l, roughness, fresnel):
+    """relight_utils.py:17-50."""
+    L = F.normalize(pts2l, dim=-1)
+    V = F.normalize(pts2c, dim=-1)
+    H = F.normalize((L + V[:, None, :]) / 2.0, dim=-1)
+    N = F.normalize(normal, dim=-1)
+    NoV = torch.sum(V * N, dim=-1, keepdim=True)
+    N = N * NoV.sign()
+    NoL = torch.sum(N[:, None, :] * L, dim=-1, keepdim=True).clamp_(1e-6, 1)
+    NoV = torch.sum(N * V, dim=-1, keepdim=True).clamp_(1e-6, 1)
+    NoH = torch.sum(N[:, None, :] * H, dim=-1, keepdim=True).clamp_(1e-6, 1)
+    VoH = torch.sum(V[:, None, :] * H, dim=-1, keepdim=True).clamp_(1e-6, 1)
+    alpha = roughness * roughness
+    alpha2 = alpha * alpha
+    k = (alpha + 2 * roughness + 1.0) / 8.0
+    FMi = ((-5.55473) * VoH - 6.98316) * VoH
+    frac0 = fresnel[:, None, :] + (1 - fresnel[:, None, :]) * torch.pow(2.0, FMi)
+    frac = frac0 * alpha2[:, None, :]
+    nom0 = NoH * NoH * (alpha2[:, None, :] - 1) + 1
+    nom1 = NoV * (1 - k) + k
+    nom2 = NoL * (1 - k[:, None, :]) + k[:, None, :]
+    nom = (4 * np.pi * nom0 * nom0 * nom1[:, None, :] * nom2).clamp_(1e-6, 4 * np.pi)
+    return frac / nom
+
+
+brdf_specular = GGX_specular
+
+
+def linear2srgb_torch(tensor_0to1):
+    """relight_utils.py:489-515; the clip of :518-533 is applied unconditionally (clamp is the identity on
+    in-range data), which removes the reference's min/max host sync."""
+    t = torch.clamp(tensor_0to1, min=0, max=1)
+    lin = t * 12.92
+    nonlin = 1.055 * torch.pow(t + 1e-6, 1 / 2.4) - (1.055 - 1)
+    return torch.where(t <= 0.0031308, lin, nonlin)
+
+
+@torch.no_grad()
+def compute_transmittance(tensoIR, surf_pts, light_in_dir, nSample=128, vis_near=0.1, vis_far=2, device='cuda'):
+    """relight_utils.py:657-705 -> (nerv_vis, nerfactor_vis): one fused density march."""
+    table = ops.equal_z_table(nSample, vis_near, vis_far, surf_pts.device)
+    t_last, acc, _ = ops.march_density(tensoIR, surf_pts, light_in_dir, table=table,
+                                       counters=tensoIR.__dict__.get("_tir_counters"))
+    return t_last, 1 - acc
+
+
+@torch.no_grad()
+def compute_radiance(tensoIR, surf_pts, light_in_dir, light_idx, nSample=128, vis_near=0.05, vis_far=1.5,
+                     device=None):
+    """relight_utils.py:777-834 -> (nerv_vis, nerfactor_vis, indirect_light)."""
+    table = ops.equal_z_table(nSample, vis_near, vis_far, surf_pts.device)
+    t_last, acc, _, rgb, _ = ops.march_radiance(tensoIR, surf_pts, light_in_dir, light_idx, table=table,
+                                                counters=tensoIR.__dict__.get("_tir_counters"))
+    return t_last, 1 - acc, rgb
+
+
+@torch.no_grad()
+def compute_secondary_shading_effects(tensoIR, surface_pts, surf2light, light_idx, nSample=96, vis_near=0.05,
+                                      vis_far=1.5, chunk_size=15000, device='cuda'):
+    """relight_utils.py:344-399 over explicit (point, direction) rays.  ``chunk_size`` is accepted and
+    ignored: the fused march never materialises [rays, samples, 3]."""
+    vis, _, ind = compute_radiance(tensoIR, surface_pts, surf2light, light_idx, nSample, vis_near, vis_far)
+    return vis.reshape(-1, 1), ind.reshape(-1, 3)
+
+
+def render_with_BRDF(depth_map, normal_map, albedo_map, roughness_map, fresnel_map, rays, tensoIR, light_idx,
+                     sample_method='fixed_envirmap', chunk_size=15000, device='cuda', use_linear2srgb=True,
+                     args=None):
+    """relight_utils.py:403-483."""
+    device = depth_map.device
+    rays_o, rays_d = rays[..., :3].to(device), rays[..., 3:].to(device)
+    surface_xyz = rays_o + depth_map.unsqueeze(-1) * rays_d
+    light_area_weight = tensoIR.light_area_weight.to(device)
+    incident_light_dirs = tensoIR.gen_light_incident_dirs(method=sample_method).to(device)   # host draws, ref order
+    bs, nlights = surface_xyz.shape[0], incident_light_dirs.shape[0]
+    surf2c = safe_l2_normalize(-rays_d, dim=-1)
+    surf2l = incident_light_dirs.reshape(1, -1, 3).expand(bs, -1, -1)
+    cosine = torch.clamp(torch.einsum("jk,ik->ij", incident_light_dirs, normal_map), min=0.0)
+    # secondary rays: cosine test + 96-sample march + appearance MLP, generated on chip per (point, direction)
+    vis, indirect, _ = ops.secondary_radiance(
+        tensoIR, surface_xyz, normal_map, light_idx, incident_light_dirs,
+        n_sample=args.second_nSample, near=args.second_near, far=args.second_far,
+        counters=tensoIR.__dict__.get("_tir_counters"))
+    specular = GGX_specular(normal_map, surf2c, surf2l, roughness_map, fresnel_map)
+    surface_brdf = albedo_map.unsqueeze(1).expand(-1, nlights, -1) / np.pi + specular
+    envir_map_light_rgbs = tensoIR.get_light_rgbs(incident_light_dirs, device=device).to(device)
+    direct_light_rgbs = torch.index_select(envir_map_light_rgbs, dim=0, index=light_idx.reshape(-1).long())
+    light_rgbs = vis * direct_light_rgbs + indirect
+    if sample_method == 'stratifed_sample_equal_areas':
+        rgb_with_brdf = torch.mean(4 * torch.pi * surface_brdf * light_rgbs * cosine[:, :, None], dim=1)
+    else:
+        rgb_with_brdf = torch.sum(surface_brdf * light_rgbs * cosine[:, :, None] * light_area_weight[None, :, None],
+                                  dim=1)
+    rgb_with_brdf = torch.clamp(rgb_with_brdf, min=0.0, max=1.0)
+    if use_linear2srgb and rgb_with_brdf.shape[0] > 0:
+        rgb_with_brdf = linear2srgb_torch(rgb_with_brdf)
+    return rgb_with_brdf

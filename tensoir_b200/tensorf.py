@@ -1,0 +1,172 @@
+"""TensorVMSplit — host-side mirror of models/tensoRF_rotated_lights.py,
+models/tensoRF_general_multi_lights.py (pass ``light_name_list=``) and, as ``TensorVMSplitInit``,
+models/tensoRF_init.py:139-305.  Parameters keep the reference layout and state_dict keys:
+density_plane.{k} [1,C,G[m1],G[m0]], density_line.{k} [1,C,G[v],1], app_plane/app_line, basis_mat.weight,
+light_line.weight, renderModule*.mlp.{0,2,4}.{weight,bias}, lgtSGs.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from . import ops, vm_autograd
+from .tensorbase import TensorBase, AlphaGridMask, raw2alpha  # noqa: F401  (re-exported like the reference)
+
+
+class TensorVMSplit(TensorBase):
+    def __init__(self, aabb, gridSize, device, **kargs):
+        super().__init__(aabb, gridSize, device, **kargs)
+
+    # ---- parameters (tensoRF_rotated_lights.py:11-29) ------------------------------------
+    def init_svd_volume(self, res, device):
+        self.density_plane, self.density_line = self.init_one_svd(self.density_n_comp, self.gridSize, 0.1, device)
+        self.app_plane, self.app_line = self.init_one_svd(self.app_n_comp, self.gridSize, 0.1, device)
+        self.basis_mat = torch.nn.Linear(sum(self.app_n_comp), self.app_dim, bias=False).to(device)
+        self.light_line = torch.nn.Embedding(self.light_num, sum(self.app_n_comp)).to(device)
+
+    def init_one_svd(self, n_component, gridSize, scale, device):
+        plane_coef, line_coef = [], []
+        for i in range(len(self.vecMode)):
+            vec_id = self.vecMode[i]
+            mat_id_0, mat_id_1 = self.matMode[i]
+            plane_coef.append(torch.nn.Parameter(
+                scale * torch.randn((1, n_component[i], gridSize[mat_id_1], gridSize[mat_id_0]))))
+            line_coef.append(torch.nn.Parameter(scale * torch.randn((1, n_component[i], gridSize[vec_id], 1))))
+        return torch.nn.ParameterList(plane_coef).to(device), torch.nn.ParameterList(line_coef).to(device)
+
+    def get_optparam_groups(self, lr_init_spatialxyz=0.02, lr_init_network=0.001):
+        """tensoRF_rotated_lights.py:33-57 (general variant :45-46)."""
+        grad_vars = [{'params': self.density_line, 'lr': lr_init_spatialxyz},
+                     {'params': self.density_plane, 'lr': lr_init_spatialxyz},
+                     {'params': self.app_line, 'lr': lr_init_spatialxyz},
+                     {'params': self.app_plane, 'lr': lr_init_spatialxyz},
+                     {'params': self.basis_mat.parameters(), 'lr': lr_init_network}]
+        if hasattr(self, "light_line"):
+            grad_vars += [{'params': self.light_line.parameters(), 'lr': 0.001}]
+        if hasattr(self, "lgtSGs_list"):
+            for p in self.lgtSGs_list:
+                grad_vars += [{'params': p, 'lr': 0.001}]
+        elif hasattr(self, "lgtSGs"):
+            grad_vars += [{'params': self.lgtSGs, 'lr': 0.001}]
+        grad_vars += [{'params': self.renderModule.parameters(), 'lr': lr_init_network}]
+        if hasattr(self, "renderModule_brdf"):
+            grad_vars += [{'params': self.renderModule_brdf.parameters(), 'lr': lr_init_network}]
+        if hasattr(self, "renderModule_normal") and self.normals_kind in (
+                "purely_predicted", "derived_plus_predicted", "residue_prediction"):
+            grad_vars += [{'params': self.renderModule_normal.parameters(), 'lr': lr_init_network}]
+        return grad_vars
+
+    # ---- regularisers (parameter-only; tensoRF_rotated_lights.py:60-92) -----------------
+    def vectorDiffs(self, vector_comps):
+        total = 0
+        for idx in range(len(vector_comps)):
+            n_comp, n_size = vector_comps[idx].shape[1:-1]
+            v = vector_comps[idx].view(n_comp, n_size)
+            dotp = torch.matmul(v, v.transpose(-1, -2))
+            non_diagonal = dotp.view(-1)[1:].view(n_comp - 1, n_comp + 1)[..., :-1]
+            total = total + torch.mean(torch.abs(non_diagonal))
+        return total
+
+    def vector_comp_diffs(self):
+        return self.vectorDiffs(self.density_line) + self.vectorDiffs(self.app_line)
+
+    def density_L1(self):
+        total = 0
+        for idx in range(len(self.density_plane)):
+            total = total + torch.mean(torch.abs(self.density_plane[idx])) + torch.mean(torch.abs(self.density_line[idx]))
+        return total
+
+    def TV_loss_density(self, reg):
+        total = 0
+        for idx in range(len(self.density_plane)):
+            total = total + reg(self.density_plane[idx]) * 1e-2
+        return total
+
+    def TV_loss_app(self, reg):
+        total = 0
+        for idx in range(len(self.app_plane)):
+            total = total + reg(self.app_plane[idx]) * 1e-2
+        return total
+
+    # ---- VM gathers (kernel-backed, differentiable w.r.t. the factors) -------------------
+    def compute_densityfeature(self, xyz_sampled):
+        """tensoRF_rotated_lights.py:95-110."""
+        return vm_autograd.density_feature(self, xyz_sampled)
+
+    def compute_densityfeature_with_xyz_grad(self, xyz_sampled):
+        """tensoRF_rotated_lights.py:113-129; the spatial gradient is available from
+        vm_autograd.density_feature_and_grad (analytic, no autograd.grad round trip)."""
+        return vm_autograd.density_feature_and_grad(self, xyz_sampled)[0]
+
+    def _light_rows(self, light_idx, n):
+        if light_idx is None:
+            return None
+        return self.light_line(light_idx.reshape(-1).to(self.light_line.weight.device))
+
+    def _mean_light(self):
+        idx = torch.arange(self.light_num, device=self.light_line.weight.device, dtype=torch.int32)
+        return torch.mean(self.light_line(idx), dim=0)
+
+    def compute_bothfeature(self, xyz_sampled, light_idx):
+        """tensoRF_rotated_lights.py:132-165 -> (radiance_field_feat, intrinsic_feat)."""
+        prod = vm_autograd.app_products(self, xyz_sampled)          # [n, 3*C] = plane*line
+        rad = self.basis_mat(prod * self._light_rows(light_idx, prod.shape[0]))
+        intr = self.basis_mat(prod * self._mean_light()[None, :])
+        return rad, intr
+
+    def compute_intrinfeature(self, xyz_sampled):
+        """tensoRF_rotated_lights.py:167-195."""
+        prod = vm_autograd.app_products(self, xyz_sampled)
+        return self.basis_mat(prod * self._mean_light()[None, :])
+
+    def compute_appfeature(self, xyz_sampled, light_idx):
+        """tensoRF_rotated_lights.py:197-224."""
+        prod = vm_autograd.app_products(self, xyz_sampled)
+        return self.basis_mat(prod * self._light_rows(light_idx, prod.shape[0]))
+
+    # ---- grid maintenance (tensoRF_rotated_lights.py:226-288) ---------------------------
+    @torch.no_grad()
+    def up_sampling_VM(self, plane_coef, line_coef, res_target):
+        for i in range(len(self.vecMode)):
+            vec_id = self.vecMode[i]
+            mat_id_0, mat_id_1 = self.matMode[i]
+            plane_coef[i] = torch.nn.Parameter(F.interpolate(plane_coef[i].data,
+                                                             size=(res_target[mat_id_1], res_target[mat_id_0]),
+                                                             mode='bilinear', align_corners=True))
+            line_coef[i] = torch.nn.Parameter(F.interpolate(line_coef[i].data, size=(res_target[vec_id], 1),
+                                                            mode='bilinear', align_corners=True))
+        return plane_coef, line_coef
+
+    @torch.no_grad()
+    def upsample_volume_grid(self, res_target):
+        self.app_plane, self.app_line = self.up_sampling_VM(self.app_plane, self.app_line, res_target)
+        self.density_plane, self.density_line = self.up_sampling_VM(self.density_plane, self.density_line, res_target)
+        self.update_stepSize(res_target)
+        print(f'upsamping to {res_target}')
+
+    @torch.no_grad()
+    def shrink(self, new_aabb):
+        print("====> shrinking ...")
+        xyz_min, xyz_max = new_aabb
+        t_l, b_r = (xyz_min - self.aabb[0]) / self.units, (xyz_max - self.aabb[0]) / self.units
+        t_l, b_r = torch.round(torch.round(t_l)).long(), torch.round(b_r).long() + 1
+        b_r = torch.stack([b_r, self.gridSize]).amin(0)
+        for i in range(len(self.vecMode)):
+            mode0 = self.vecMode[i]
+            self.density_line[i] = torch.nn.Parameter(self.density_line[i].data[..., t_l[mode0]:b_r[mode0], :])
+            self.app_line[i] = torch.nn.Parameter(self.app_line[i].data[..., t_l[mode0]:b_r[mode0], :])
+            mode0, mode1 = self.matMode[i]
+            self.density_plane[i] = torch.nn.Parameter(
+                self.density_plane[i].data[..., t_l[mode1]:b_r[mode1], t_l[mode0]:b_r[mode0]])
+            self.app_plane[i] = torch.nn.Parameter(
+                self.app_plane[i].data[..., t_l[mode1]:b_r[mode1], t_l[mode0]:b_r[mode0]])
+        if not torch.all(self.alphaMask.gridSize == self.gridSize):
+            t_l_r, b_r_r = t_l / (self.gridSize - 1), (b_r - 1) / (self.gridSize - 1)
+            correct_aabb = torch.zeros_like(new_aabb)
+            correct_aabb[0] = (1 - t_l_r) * self.aabb[0] + t_l_r * self.aabb[1]
+            correct_aabb[1] = (1 - b_r_r) * self.aabb[0] + b_r_r * self.aabb[1]
+            print("aabb", new_aabb, "\ncorrect aabb", correct_aabb)
+            new_aabb = correct_aabb
+        newSize = b_r - t_l
+        self.aabb = new_aabb
+        self.update_stepSize((newSize[0], newSize[1], newSize[2]))

@@ -1,0 +1,266 @@
+"""GPU parity: the CUDA path (through the C ABI) vs the reference-generated golden fixtures and the oracle.
+
+Tolerances: fp32 path, north-star bar 1e-4 relative on rendered maps.  Counts (mask / density / app samples)
+must match the oracle exactly on these fixtures."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import tensoir_oracle as O            # noqa: E402
+from helpers import oracle_field, named_oracle_params   # noqa: E402
+from gpu_helpers import model_from_fixture, renderer_args   # noqa: E402
+
+DEV = "cuda:0"
+TOL = 1e-4
+
+
+def close(got, want, tol=TOL, what=""):
+    got = got.detach().float().cpu()
+    want = want.detach().float().cpu()
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    err = (got - want).abs()
+    bound = tol * (1.0 + want.abs())
+    assert bool((err <= bound).all()), (what, float(err.max()), float((err / bound).max()))
+
+
+@pytest.fixture(scope="module")
+def rot(golden_rotated):
+    from tensoir_b200 import _lib
+    _lib.load()
+    return golden_rotated, model_from_fixture(golden_rotated, DEV)
+
+
+def test_unit_kernels(rot):
+    from tensoir_b200 import ops
+    fx, m = rot
+    pts = fx["pts"].to(DEV)
+    xn = m.normalize_coord(pts)
+    assert torch.equal(ops.alpha_mask_points(m, pts).cpu(), fx["sample_alpha"] > 0)
+    feat, sig = ops.density_points(m, xn)
+    close(feat, fx["density_feature"], 2e-5, "density_feature")
+    close(sig, fx["sigma"], 2e-5, "sigma")
+    close(m.compute_densityfeature(xn), fx["density_feature"], 2e-5)
+    li = fx["li"].to(DEV)
+    rad, intr = m.compute_bothfeature(xn, li)
+    close(rad, fx["rad_feat"], 2e-5, "rad")
+    close(intr, fx["intr_feat"], 2e-5, "intr")
+    close(m.compute_appfeature(xn, li), fx["app_feat"], 2e-5)
+    close(m.compute_intrinfeature(xn), fx["intrin_only"], 2e-5)
+    vd = fx["viewdirs"].to(DEV)
+    close(ops.app_mlp_points(m, xn, vd, li, head="renderModule"), fx["mlp_rgb"], 2e-5, "mlp_rgb")
+    close(ops.app_mlp_points(m, xn, xn, None, head="renderModule_brdf", light="mean"), fx["mlp_brdf"], 2e-5, "brdf")
+    close(ops.app_mlp_points(m, xn, xn, None, head="renderModule_normal", light="mean"), fx["mlp_normal"], 2e-5, "nrm")
+    from tensoir_b200.primary import _derived_normals
+    close(_derived_normals(m, fx["xj"].to(DEV)), fx["derived_normals"], 5e-4, "derived_normals")
+
+
+def test_valid_sample_lists_bit_exact(rot):
+    """sample_ray + bbox + alpha-mask filter: indices must equal the reference's masks exactly."""
+    from tensoir_b200 import vm_autograd as vm
+    fx, m = rot
+    f = oracle_field(fx)
+    rays = fx["rays"]
+    for is_train, ns, jit in ((False, -1, None), (True, 40, fx["jitter40"])):
+        pts, z, valid = O.sample_ray(f, rays[:, :3], rays[:, 3:6], is_train, ns, jitter=jit)
+        valid = O._refine_valid(f, pts, valid)
+        lst = vm.valid_samples(m, rays[:, :3].to(DEV), rays[:, 3:6].to(DEV), n_samples=ns,
+                               jitter=None if jit is None else jit.to(DEV))
+        idx = valid.nonzero()
+        assert torch.equal(lst["ray"].cpu().long(), idx[:, 0])
+        assert torch.equal(lst["sample"].cpu().long(), idx[:, 1])
+        assert torch.equal(lst["z"].cpu(), z.expand(valid.shape)[valid])
+        assert torch.equal(lst["xn"].cpu(), O.normalize_coord(f, pts)[valid])
+
+
+def test_secondary_marches(rot):
+    from tensoir_b200 import ops, relight_utils as RU
+    fx, m = rot
+    f = oracle_field(fx)
+    surf, dirs, li2 = fx["surf"].to(DEV), fx["dirs"].to(DEV), fx["li2"].to(DEV)
+    cnt = ops.new_counters(DEV)
+    m.__dict__["_tir_counters"] = cnt
+    nerv, nerf = RU.compute_transmittance(m, surf, dirs, nSample=96, vis_near=0.05, vis_far=1.5)
+    close(nerv, fx["transmittance"][0], 2e-5, "nerv_vis")
+    close(nerf, fx["transmittance"][1], 2e-5, "nerfactor_vis")
+    O.compute_transmittance(f, fx["surf"], fx["dirs"], 96, 0.05, 1.5)
+    c = ops.counters_dict(cnt)
+    assert c["density"] == f.counters["density"] and c["mask"] == f.counters["mask"]
+    cnt.zero_()
+    f.counters.clear()
+    nerv, nerf, ind = RU.compute_radiance(m, surf, dirs, li2, nSample=96, vis_near=0.05, vis_far=1.5)
+    close(nerv, fx["radiance"][0], 2e-5)
+    close(nerf, fx["radiance"][1], 2e-5)
+    close(ind, fx["radiance"][2], TOL, "indirect")
+    *_, valid, app_mask, weight = O.compute_radiance(f, fx["surf"], fx["dirs"], fx["li2"], 96, 0.05, 1.5,
+                                                     return_aux=True)
+    c = ops.counters_dict(cnt)
+    assert c["overflow"] == 0
+    assert (c["mask"], c["density"], c["app"]) == (f.counters["mask"], f.counters["density"], f.counters["app"])
+    # the compacted sample list holds exactly the reference's app_mask indices
+    sm = m.__dict__["_tir_scratch"].samples()
+    key = (sm["ray"].long() * 96 + sm["sample"].long()).cpu().sort().values
+    want = app_mask.nonzero()
+    assert torch.equal(key, (want[:, 0] * 96 + want[:, 1]).sort().values)
+    del m.__dict__["_tir_counters"]
+
+
+def test_dense_secondary_vs_explicit(rot):
+    """tir_secondary_radiance (rays generated on chip) == compute_radiance on the expanded ray list."""
+    from tensoir_b200 import ops
+    fx, m = rot
+    f = oracle_field(fx)
+    g = torch.Generator().manual_seed(4)
+    pts = (torch.rand(7, 3, generator=g) * 2 - 1) * 0.9
+    nrm = torch.nn.functional.normalize(torch.randn(7, 3, generator=g), dim=-1)
+    li = (torch.arange(7) % 2).view(-1, 1).to(torch.int32)
+    dirs = fx["fixed_dirs"]
+    vis, ind, _ = ops.secondary_radiance(m, pts.to(DEV), nrm.to(DEV), li.to(DEV), dirs.to(DEV), n_sample=24)
+    cos = torch.clamp(torch.einsum("jk,ik->ij", dirs, nrm), min=0)
+    mask = cos > 1e-6
+    P = pts[:, None, :].expand(-1, dirs.shape[0], -1)[mask]
+    D = dirs[None].expand(7, -1, -1)[mask]
+    L = li.view(-1, 1, 1).expand(-1, dirs.shape[0], 1)[mask]
+    v, _, i = O.compute_radiance(f, P, D, L, 24, 0.05, 1.5)
+    want_v = torch.zeros(7, dirs.shape[0], 1)
+    want_i = torch.zeros(7, dirs.shape[0], 3)
+    want_v[mask] = v[:, None]
+    want_i[mask] = i
+    close(vis, want_v, 2e-5, "vis")
+    close(ind, want_i, TOL, "indirect")
+
+
+def test_primary_eval(rot):
+    fx, m = rot
+    rays, li = fx["rays"].to(DEV), fx["light_idx"].to(DEV)
+    torch.manual_seed(101)
+    m.__dict__["_tir_randn_like"] = lambda t: torch.randn(t.shape).to(t.device)
+    with torch.no_grad():
+        got = m(rays, li, white_bg=True, is_train=False, is_relight=True, N_samples=-1)
+    names = ["rgb", "depth", "normal", "albedo", "rough", "fresnel", "acc", "ndiff", "norient", "acc_mask",
+             "alb_loss", "rough_loss"]
+    for n, g, w in zip(names, got, fx["primary_eval"]):
+        if w.dtype == torch.bool:
+            assert torch.equal(g.cpu(), w), n
+        else:
+            close(g, w, TOL, n)
+    with torch.no_grad():
+        got = m(rays, li, white_bg=True, is_train=False, is_relight=False, N_samples=-1)
+    for n, g, w in zip(names, got, fx["primary_eval_norelight"]):
+        if w is None:
+            assert g is None
+        else:
+            close(g, w, TOL, n)
+    del m.__dict__["_tir_randn_like"]
+
+
+def test_boundary_eval(rot):
+    from tensoir_b200 import Renderer_TensoIR_train
+    fx, m = rot
+    torch.manual_seed(102)
+    m.__dict__["_tir_randn_like"] = lambda t: torch.randn(t.shape).to(t.device)
+    with torch.no_grad():
+        got = Renderer_TensoIR_train(fx["rays"], None, fx["light_idx"], m, N_samples=-1, white_bg=True,
+                                     is_train=False, is_relight=True, sample_method='fixed_envirmap',
+                                     chunk_size=160000, device=DEV, args=renderer_args(24))
+    for k, w in fx["renderer_eval"].items():
+        close(got[k], w, TOL, k)
+    del m.__dict__["_tir_randn_like"]
+
+
+def test_boundary_train_step_grads(golden_rotated):
+    """Full training-mode boundary + backward: outputs, loss and every parameter gradient vs the reference."""
+    from tensoir_b200 import Renderer_TensoIR_train
+    fx = golden_rotated
+    m = model_from_fixture(fx, DEV)
+    m.__dict__["_tir_randn_like"] = lambda t: torch.randn(t.shape).to(t.device)   # CPU stream like the oracle run
+    torch.manual_seed(fx["train_seed"])
+    got = Renderer_TensoIR_train(fx["rays"], None, fx["light_idx"], m, N_samples=60, white_bg=True, is_train=True,
+                                 is_relight=True, sample_method='stratified_sampling', chunk_size=160000,
+                                 device=DEV, args=renderer_args(24))
+    for k, w in fx["renderer_train"].items():
+        close(got[k], w, TOL, k)
+    target = torch.full_like(got["rgb_map"], 0.5)
+    loss = (((got["rgb_map"] - target) ** 2).mean() + 0.2 * ((got["rgb_with_brdf_map"] - target) ** 2).mean()
+            + 0.0005 * got["normals_diff_map"].mean() + 0.001 * got["normals_orientation_loss_map"].mean()
+            + 0.001 * got["albedo_smoothness_loss"] + 0.001 * got["roughness_smoothness_loss"])
+    loss.backward()
+    close(loss, fx["renderer_train_loss"], TOL, "loss")
+    n = 0
+    for k, p in m.named_parameters():
+        w = fx["renderer_train_grads"][k]
+        if w is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            continue
+        g = p.grad.detach().cpu()
+        scale = float(w.abs().max()) + 1e-12
+        err = float((g - w).abs().max()) / scale
+        assert err < 2e-3, (k, err)
+        n += 1
+    assert n >= 20
+
+
+def test_general_and_init_models(golden_general, golden_init):
+    from tensoir_b200 import Renderer_TensoIR_train, OctreeRender_trilinear_fast
+    fx = golden_general
+    m = model_from_fixture(fx, DEV)
+    torch.manual_seed(103)
+    m.__dict__["_tir_randn_like"] = lambda t: torch.randn(t.shape).to(t.device)
+    with torch.no_grad():
+        got = Renderer_TensoIR_train(fx["rays"], None, fx["light_idx"], m, N_samples=-1, white_bg=True,
+                                     is_train=False, is_relight=True, sample_method='fixed_envirmap',
+                                     chunk_size=160000, device=DEV, args=renderer_args(16))
+    for k, w in fx["renderer_eval"].items():
+        close(got[k], w, TOL, k)
+    fx = golden_init
+    for with_mask, key in ((False, "forward_nomask"), (True, "forward_mask")):
+        mi = model_from_fixture(fx, DEV, with_mask=with_mask)
+        with torch.no_grad():
+            rgb, _, depth, _, _ = OctreeRender_trilinear_fast(fx["rays"], mi, chunk=40, N_samples=32, white_bg=True,
+                                                              is_train=False, device=DEV)
+        close(rgb, fx[key][0], TOL, "rgb")
+        close(depth, fx[key][1], TOL, "depth")
+
+
+def test_update_alpha_mask_and_filtering(golden_rotated):
+    fx = golden_rotated
+    m = model_from_fixture(fx, DEV, with_mask=False)
+    new_aabb = m.updateAlphaMask((24, 24, 24))
+    assert torch.equal(m.alphaMask.alpha_volume.cpu(), fx["alpha_volume"])
+    close(new_aabb, fx["new_aabb"], 1e-6)
+    rays = fx["rays"]
+    kept, mask = m.filtering_rays(rays, bbox_only=True)
+    assert kept.shape[0] == int(mask.sum())
+    f = oracle_field(fx)
+    pts, _, _ = O.sample_ray(f, rays[:, :3], rays[:, 3:6], False, 256)
+    want = (O.sample_alpha(f, pts.reshape(-1, 3)).view(pts.shape[:-1]) > 0).any(-1)
+    _, mask2 = m.filtering_rays(rays, N_samples=256)
+    assert torch.equal(mask2, want)
+
+
+def test_full_size_properties():
+    """BASELINE-size checks through size-independent properties: 128^3 lego scene, 4096-ray batch.
+    (i) T_last * prod == consistency: nerv_vis in [0,1], nerfactor_vis = 1 - acc; (ii) chunking invariance:
+    marching the batch in two halves gives the same per-ray results bit-for-bit; (iii) counters add up."""
+    from tensoir_b200 import TensorVMSplit, ops
+    from tensoir_b200.synthetic import install_lego_density, hemisphere_poses, training_batch
+    torch.manual_seed(20211202)
+    aabb = torch.tensor([[-1.5] * 3, [1.5] * 3], device=DEV)
+    m = TensorVMSplit(aabb, [128] * 3, DEV, density_n_comp=[16] * 3, appearance_n_comp=[48] * 3, app_dim=27,
+                      shadingMode='MLP_Fea', step_ratio=0.5, normals_kind='derived_plus_predicted',
+                      light_rotation=['000'], light_kind='sg', alphaMask_thres=0.001)
+    install_lego_density(m)
+    m.updateAlphaMask((128, 128, 128))
+    rays, _ = training_batch(hemisphere_poses(100), 4096, 0)
+    rays = rays.to(DEV)
+    cnt = ops.new_counters(DEV)
+    t, acc, dep = ops.march_density(m, rays[:, :3], rays[:, 3:], n_samples=443, counters=cnt)
+    assert float(t.min()) >= 0 and float(t.max()) <= 1 + 1e-6 and float(acc.max()) <= 1 + 1e-5
+    t1, a1, d1 = ops.march_density(m, rays[:2048, :3], rays[:2048, 3:], n_samples=443)
+    t2, a2, d2 = ops.march_density(m, rays[2048:, :3], rays[2048:, 3:], n_samples=443)
+    assert torch.equal(torch.cat([t1, t2]), t) and torch.equal(torch.cat([a1, a2]), acc)
+    c = ops.counters_dict(cnt)
+    assert c["rays"] == 4096 and 0 < c["density"] <= c["mask"] <= 4096 * 443
+    hit = acc > 0.5
+    assert 0.05 < float(hit.float().mean()) < 0.95
+    close(t[hit], torch.zeros_like(t[hit]), 1e-3)       # opaque boxes: sigma = 20 -> T -> 0 behind the first surface
