@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py — the driver's benchmark contract for tensoir_b200.
+
+Step = one training step of the relight phase on one 4096-ray batch of the synthetic lego-shaped scene
+(BASELINE.json configs[1]: single light, 800x800 x 100 train views, full VM grid + BRDF MLPs):
+    Renderer_TensoIR_train(is_train=True, is_relight=True, stratified_sampling)   primary + secondary marches
+    + loss assembly of train_tensoIR.py:262-312 + backward + Adam step.
+Metric = (primary + secondary rays marched) / second, whole job.  `--impl reference` times the reference's
+algorithm (the oracle port under oracle/, the only part of this file that may execute oracle/) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch                      # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = "primary+secondary rays/sec (800x800 lego-shaped synthetic, relight training step)"
+UNIT = "rays/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", type=int, default=300)
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--cpu-rays", type=int, default=1024, help="bounded CPU-baseline sample (primary rays / step)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class Args:   # the three fields render_with_BRDF reads from the train scripts' namespace (opt.py:150-154)
+    second_nSample, second_near, second_far = 96, 0.05, 1.5
+
+
+def loss_of(ret, target, model, it=0):
+    """Loss assembly of the relight phase, train_tensoIR.py:262-312 (TV is switched off once relight starts,
+    :396-399; weights from configs/single_light/armadillo.txt)."""
+    loss = torch.mean((ret['rgb_map'] - target) ** 2)
+    loss = loss + 4e-5 * model.density_L1()
+    loss = loss + 0.2 * torch.mean((ret['rgb_with_brdf_map'] - target) ** 2)
+    loss = loss + 0.0005 * ret['normals_diff_map'].mean() + 0.001 * ret['normals_orientation_loss_map'].mean()
+    loss = loss + 0.001 * ret['roughness_smoothness_loss'] + 0.001 * ret['albedo_smoothness_loss']
+    return loss
+
+
+class ClockSampler:
+    """nvidia-smi sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace('.', '').isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace('.', '').isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for j, nm in enumerate(names):
+                if len(r) > 5 + j and r[5 + j].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(n):
+    if n > 1 or "RANK" in os.environ:
+        rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+        local = int(os.environ.get("LOCAL_RANK", rank))
+        return rank, world, local
+    return 0, 1, 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_reference(a, rank, world):
+    """The reference's own algorithm on the host CPU cores (oracle port), bounded sample per step."""
+    if rank != 0:
+        return
+    out = cpu_baseline(a, steps=a.steps, warmup=a.warmup)
+    line = {"metric": METRIC, "value": out["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": out["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": workload_config(a, parallelism=f"cpu{out['cores']}"),
+            "cpu_baseline": {"value": out["value"], "unit": UNIT, "cores": out["cores"], "kind": "port",
+                             "sample": out["sample"]},
+            "e2e": {"value": out["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(a, parallelism):
+    from tensoir_b200.synthetic import n_samples_for
+    return {"workload": f"relight training step, lego-shaped synthetic scene (BASELINE configs[1] shape): "
+                        f"TensorVMSplit {a.grid}^3 (16/48 comps, 3 MLP heads, SG light), batch {a.batch} rays of "
+                        f"100 views 800x800, N_samples {n_samples_for(a.grid)}, 16x32 stratified secondary dirs x 96 "
+                        f"samples, fwd+bwd+Adam", "global_batch_rays": a.batch * max(1, a.gpus),
+            "grid": a.grid, "parallelism": parallelism,
+            "l2": "inputs change every step (new ray batch, updated parameters); VM tensors "
+                  f"({'exceed' if a.grid >= 256 else 'fit in'} L2 at this grid)"}
+
+
+def cpu_baseline(a, steps=2, warmup=1):
+    """Oracle (port of the reference) fwd+bwd+Adam on a bounded sample of the same workload."""
+    from oracle import tensoir_oracle as O
+    from helpers import named_oracle_params  # noqa: F401
+    from tensoir_b200.synthetic import make_lego_state, hemisphere_poses, training_batch, n_samples_for
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    f = make_lego_state(a.grid)
+    for p in f.parameters():
+        p.requires_grad_(True)
+    opt = torch.optim.Adam([{"params": f.parameters(), "lr": 1e-3}], betas=(0.9, 0.99))
+    poses = hemisphere_poses(100)
+    n_s = n_samples_for(a.grid)
+    rays_total, t_total = 0, 0.0
+    for it in range(warmup + steps):
+        rays, li = training_batch(poses, a.cpu_rays, it)
+        f.counters.clear()
+        t0 = time.perf_counter()
+        ret = O.renderer_train(f, rays, li, n_s, True, True, True, 'stratified_sampling', 160000, 96, 0.05, 1.5)
+        target = torch.full_like(ret["rgb_map"], 0.5)
+        loss = torch.mean((ret['rgb_map'] - target) ** 2) + 0.2 * torch.mean((ret['rgb_with_brdf_map'] - target) ** 2)
+        loss = loss + 0.0005 * ret['normals_diff_map'].mean() + 0.001 * ret['normals_orientation_loss_map'].mean()
+        loss = loss + 0.001 * ret['roughness_smoothness_loss'] + 0.001 * ret['albedo_smoothness_loss']
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            rays_total += a.cpu_rays + f.counters.get("secondary_rays", 0)
+            t_total += dt
+    return {"value": rays_total / t_total, "ms_per_step": 1e3 * t_total / max(steps, 1), "cores": cores,
+            "sample": f"{a.cpu_rays} primary rays/step x {steps} steps of the same workload (oracle port, "
+                      f"torch CPU, {cores} threads)"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def main():
+    a = parse()
+    rank, world, local = dist_setup(a.gpus)
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+        return
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback for the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import __graft_entry__ as g
+    if rank == 0:
+        g.build()
+    if world > 1:
+        dist.barrier()
+    from tensoir_b200 import Renderer_TensoIR_train, _lib, ops
+    from tensoir_b200.dp import GradBucket, broadcast_parameters
+    from tensoir_b200.synthetic import make_lego_model, hemisphere_poses, training_batch, n_samples_for
+    _lib.load()
+
+    model = make_lego_model(a.grid, dev)
+    broadcast_parameters(model.parameters())
+    params = [p for grp in model.get_optparam_groups(0.02, 0.001) for p in (grp["params"] if isinstance(
+        grp["params"], (list, tuple, torch.nn.ParameterList)) else list(grp["params"]))]
+    opt = torch.optim.Adam(model.get_optparam_groups(0.02, 0.001), betas=(0.9, 0.99))
+    bucket = GradBucket(params) if world > 1 else None
+    poses = hemisphere_poses(100)
+    n_s = n_samples_for(a.grid)
+    total = a.warmup + a.steps
+    # weak scaling: every rank draws its own 4096-ray batch each step (global batch = batch * world)
+    host_batches = [training_batch(poses, a.batch, it * world + rank) for it in range(2 * total)]
+    pinned = [(r.pin_memory(), l.pin_memory()) for r, l in host_batches]
+    target = torch.full((a.batch, 3), 0.5, device=dev)
+    counters = ops.new_counters(dev)
+    model.__dict__["_tir_counters"] = counters
+
+    def step(rays, li):
+        ret = Renderer_TensoIR_train(rays, None, li, model, N_samples=n_s, white_bg=True, is_train=True,
+                                     is_relight=True, sample_method='stratified_sampling', chunk_size=160000,
+                                     device=dev, args=Args)
+        loss = loss_of(ret, target, model)
+        opt.zero_grad(set_to_none=False)
+        loss.backward()
+        if bucket is not None:
+            bucket.all_reduce_mean()
+        opt.step()
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_region(batches, read_loss):
+        counters.zero_()
+        launches0 = _lib.launch_count
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for rays, li in batches:
+            loss = step(rays, li)
+            if read_loss:
+                loss.item()                       # device -> host read of the step's result
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        c = counters.clone()
+        if world > 1:
+            dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        return float(t.item()), ops.counters_dict(c), _lib.launch_count - launches0
+
+    # ---- device-resident arm: inputs already in HBM when the timed region starts
+    dev_batches = [(r.to(dev), l.to(dev)) for r, l in host_batches[:total]]
+    for rays, li in dev_batches[:a.warmup]:
+        step(rays, li)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms, cnt, launches = timed_region(dev_batches[a.warmup:], read_loss=False)
+    rays_total = a.batch * a.steps * world + (cnt["rays"] - a.batch * a.steps * world)   # primary + secondary
+    rays_total = cnt["rays"]          # TIR_CNT_RAYS counts every marched ray: primary (valid-list pass) + secondary
+    value = rays_total / (ms * 1e-3)
+
+    # ---- end-to-end arm: pinned HOST buffers through the public boundary, loss read back every step
+    for rays, li in pinned[total:total + a.warmup]:
+        step(rays, li)
+    ms_e2e, cnt_e2e, _ = timed_region(pinned[total + a.warmup:2 * total], read_loss=True)
+    clk = clocks.stop() if rank == 0 else None
+    e2e_value = cnt_e2e["rays"] / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (the secondary march), timed live with CUDA events on the launch stream
+    roof = roofline(model, dev_batches[-1], n_s, dev, a)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(a, f"dp{world}"),
+            "primary_rays_per_s": a.batch * a.steps * world / (ms * 1e-3),
+            "secondary_rays_per_s": (cnt["rays"] - a.batch * a.steps * world) / (ms * 1e-3),
+            "counters_per_step": {k: v / a.steps for k, v in cnt.items()},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
+                    "h2d_bytes_per_step": a.batch * (6 * 4 + 4) * world, "d2h_bytes_per_step": 4 * world},
+            "gpu_launches": launches, "clocks": clk, "roofline": roof}
+    if not a.no_cpu_baseline and world == 1:
+        cb = cpu_baseline(a, steps=2, warmup=1)
+        line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": "port",
+                                "sample": cb["sample"]}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def roofline(model, batch, n_s, dev, a):
+    """achieved = algorithmic bytes / launch duration of the secondary march kernel (SURVEY.md §8d:
+    32 B per alpha-mask query + 1152 B per density sample + 16 B out per ray), CUDA events, after warm-up."""
+    from tensoir_b200 import ops
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    else:
+        peak, src = 6650.0, "fallback (B200_PROFILING.md)"
+    rays, li = batch
+    with torch.no_grad():
+        out = model(rays, li, is_train=False, is_relight=True, N_samples=n_s)
+    depth, normal, acc_mask = out[1], out[2], out[9]
+    surf = (rays[:, :3] + depth[:, None] * rays[:, 3:])[acc_mask]
+    dirs = model.gen_light_incident_dirs(method='stratified_sampling').to(dev)
+    st = ops.SecondaryStages(model, surf, normal[acc_mask], li[acc_mask], dirs)
+
+    def t(fn, n=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+    ms_march = t(st.march)
+    c = ops.counters_dict(st.counters)
+    ms_mlp = t(st.mlp)
+    b_march = 32 * c["mask"] + 1152 * c["density"] + 16 * c["rays"]
+    b_mlp = 3456 * c["app"]
+    flops_mlp = 79712 * c["app"]
+    return {"bound": "hbm", "kernel": "march_kernel<16,TABLE,app,dense> (secondary density march + compaction)",
+            "achieved": b_march / (ms_march * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+            "frac": b_march / (ms_march * 1e-3) / 1e9 / peak, "peak_source": src, "traffic": None,
+            "ms_per_launch": ms_march, "algorithmic_bytes_per_launch": b_march,
+            "units_per_launch": {"mask_queries": c["mask"], "density_samples": c["density"], "rays": c["rays"]},
+            "second_kernel": {"kernel": "app_mlp_kernel (appearance gather + basis + 150-128-128-3 MLP, fp32 SIMT)",
+                              "ms_per_launch": ms_mlp, "app_samples": c["app"],
+                              "achieved_GBps": b_mlp / (ms_mlp * 1e-3) / 1e9,
+                              "achieved_TFLOPs": flops_mlp / (ms_mlp * 1e-3) / 1e12}}
+
+
+if __name__ == "__main__":
+    main()

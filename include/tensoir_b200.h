@@ -166,6 +166,13 @@ int tir_secondary_radiance(const TirField* field, const TirMlp* mlp, const float
                            TirAppSample* samples, uint32_t* sample_count, int64_t capacity,
                            uint64_t* counters, void* stream);
 
+/* First half of tir_secondary_radiance only (cosine test + density march + app-sample compaction); the second half is
+ * tir_app_mlp on the same list.  Exposed so the two kernels can be timed / profiled separately. */
+int tir_secondary_march(const TirField* field, const float* surf_xyz, const float* normals, int64_t n_pts,
+                        const float* dirs, int32_t n_dirs, const TirMarchCfg* cfg, float* vis,
+                        TirAppSample* samples, uint32_t* sample_count, int64_t capacity,
+                        uint64_t* counters, void* stream);
+
 /* Appearance gather + basis_mat + MLPRender_Fea on a compacted sample list
  * (compute_appfeature tensoRF_rotated_lights.py:197-224 + MLPRender_Fea tensorBase:136-146):
  *   rgb_out[ray] += weight * sigmoid(mlp(...)) for every sample; dirs_of_ray gives the view dir.

@@ -69,6 +69,9 @@ EXPORTS = {
     "tir_secondary_radiance": (C.c_int, [C.POINTER(TirField), C.POINTER(TirMlp), f32p, f32p, C.c_void_p, C.c_int64,
                                          f32p, C.c_int32, C.POINTER(TirMarchCfg), f32p, f32p, C.c_void_p,
                                          C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "tir_secondary_march": (C.c_int, [C.POINTER(TirField), f32p, f32p, C.c_int64, f32p, C.c_int32,
+                                      C.POINTER(TirMarchCfg), f32p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                      C.c_void_p]),
     "tir_app_mlp": (C.c_int, [C.POINTER(TirField), C.POINTER(TirMlp), C.c_void_p, C.c_void_p, C.c_int64, f32p,
                               C.c_int32, C.c_void_p, f32p, C.c_void_p]),
     "tir_app_mlp_points": (C.c_int, [C.POINTER(TirField), C.POINTER(TirMlp), f32p, f32p, C.c_void_p, C.c_int64,
@@ -90,7 +93,38 @@ EXPORTS = {
                                     C.c_void_p]),
 }
 
+# kernels launched per entry point (for bench.py's gpu_launches claim)
+KERNELS_PER_CALL = {"tir_pack_channels_last": 1, "tir_unpack_channels_last_add": 1, "tir_pack_alpha_mask": 2,
+                    "tir_density_points": 1, "tir_alpha_mask_points": 1, "tir_march_density": 1,
+                    "tir_march_radiance": 2, "tir_secondary_march": 1, "tir_secondary_radiance": 2, "tir_app_mlp": 1,
+                    "tir_app_mlp_points": 1, "tir_vm_app_products": 1, "tir_vm_app_products_bwd": 1,
+                    "tir_vm_density_bwd": 1, "tir_vm_density_grad": 1, "tir_vm_density_grad_bwd": 1,
+                    "tir_valid_samples_count": 1, "tir_valid_samples_fill": 1, "tir_composite_fwd": 1,
+                    "tir_composite_bwd": 1}
+launch_count = 0
+
 _lib = None
+
+
+class _Counted:
+    """Thin callable that counts kernel launches per C-ABI call."""
+
+    def __init__(self, fn, k):
+        self.fn, self.k = fn, k
+
+    def __call__(self, *a):
+        global launch_count
+        launch_count += self.k
+        return self.fn(*a)
+
+
+class _LibProxy:
+    def __init__(self, cdll):
+        self._cdll = cdll
+        for name in EXPORTS:
+            fn = getattr(cdll, name)
+            k = KERNELS_PER_CALL.get(name, 0)
+            setattr(self, name, _Counted(fn, k) if k else fn)
 
 
 class TirError(RuntimeError):
@@ -114,8 +148,8 @@ def load():
     v = lib.tir_abi_version()
     if v != ABI_VERSION:
         raise TirError(f"ABI version mismatch: library {v}, binding {ABI_VERSION}")
-    _lib = lib
-    return lib
+    _lib = _LibProxy(lib)
+    return _lib
 
 
 _STATUS = {-1: "TIR_ERR_NULL", -2: "TIR_ERR_SHAPE", -3: "TIR_ERR_CONFIG", -4: "TIR_ERR_CAPACITY"}

@@ -250,13 +250,11 @@ extern "C" int tir_march_radiance(const TirField* field, const TirMlp* mlp, cons
   return tir_app_mlp(field, mlp, samples, sample_count, capacity, rays_d, 0, light_idx, rgb, stream);
 }
 
-extern "C" int tir_secondary_radiance(const TirField* field, const TirMlp* mlp, const float* surf_xyz,
-                                      const float* normals, const int32_t* light_idx, int64_t n_pts,
-                                      const float* dirs, int32_t n_dirs, const TirMarchCfg* cfg, float* vis,
-                                      float* indirect, TirAppSample* samples, uint32_t* sample_count,
-                                      int64_t capacity, uint64_t* counters, void* stream) {
-  if (!field || !mlp || !cfg || !surf_xyz || !normals || !dirs || !vis || !indirect || !samples || !sample_count)
-    return TIR_ERR_NULL;
+extern "C" int tir_secondary_march(const TirField* field, const float* surf_xyz, const float* normals,
+                                  int64_t n_pts, const float* dirs, int32_t n_dirs, const TirMarchCfg* cfg,
+                                  float* vis, TirAppSample* samples, uint32_t* sample_count, int64_t capacity,
+                                  uint64_t* counters, void* stream) {
+  if (!field || !cfg || !surf_xyz || !normals || !dirs || !vis || !samples || !sample_count) return TIR_ERR_NULL;
   if (n_dirs <= 0) return TIR_ERR_SHAPE;
   if (capacity <= 0) return TIR_ERR_CAPACITY;
   MarchParams p{};
@@ -264,7 +262,17 @@ extern "C" int tir_secondary_radiance(const TirField* field, const TirMlp* mlp, 
   p.n_rays = n_pts * (int64_t)n_dirs;
   p.t_last = vis; p.counters = (unsigned long long*)counters;
   p.samples = samples; p.sample_count = sample_count; p.capacity = capacity;
-  int rc = launch_march<true, true>(p, (cudaStream_t)stream);
+  return launch_march<true, true>(p, (cudaStream_t)stream);
+}
+
+extern "C" int tir_secondary_radiance(const TirField* field, const TirMlp* mlp, const float* surf_xyz,
+                                      const float* normals, const int32_t* light_idx, int64_t n_pts,
+                                      const float* dirs, int32_t n_dirs, const TirMarchCfg* cfg, float* vis,
+                                      float* indirect, TirAppSample* samples, uint32_t* sample_count,
+                                      int64_t capacity, uint64_t* counters, void* stream) {
+  if (!mlp || !indirect) return TIR_ERR_NULL;
+  int rc = tir_secondary_march(field, surf_xyz, normals, n_pts, dirs, n_dirs, cfg, vis, samples, sample_count,
+                               capacity, counters, stream);
   if (rc) return rc;
   return tir_app_mlp(field, mlp, samples, sample_count, capacity, dirs, n_dirs, light_idx, indirect, stream);
 }

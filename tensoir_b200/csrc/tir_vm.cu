@@ -185,19 +185,24 @@ __global__ void density_grad_kernel(TirField f, const float* __restrict__ xn, in
       const float sx = 0.5f * (W - 1), sy = 0.5f * (H - 1), sl = 0.5f * (D - 1);
       const float* P = f.dplane[k];
       const float* L = f.dline[k];
-      float s = 0.f, s0 = 0.f, s1 = 0.f, sv = 0.f;
+      // Per-tap channel sums first, then the weight combination: this is the grouping autograd produces for the
+      // reference (grad of a broadcast weight = sum over channels), and it makes flat regions give an exact 0.
+      float S[4] = {0.f, 0.f, 0.f, 0.f}, R[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int c = 0; c < C; c += 4) {
         const float4 a = ldg4(P + (size_t)b.o00 * C + c), bb = ldg4(P + (size_t)b.o01 * C + c),
                      cc = ldg4(P + (size_t)b.o10 * C + c), d = ldg4(P + (size_t)b.o11 * C + c);
         const float4 l0 = ldg4(L + (size_t)l.o0 * C + c), l1 = ldg4(L + (size_t)l.o1 * C + c);
-        const float4 pv = f4_comb4(a, bb, cc, d, b.nw, b.ne, b.sw, b.se);
-        const float4 px = f4_comb4(a, bb, cc, d, b.dx_nw, b.dx_ne, b.dx_sw, b.dx_se);
-        const float4 py = f4_comb4(a, bb, cc, d, b.dy_nw, b.dy_ne, b.dy_sw, b.dy_se);
         const float4 lv = f4_add(f4_scale(l0, l.w0), f4_scale(l1, l.w1));
         const float4 dl = f4_sub(l1, l0);
-        s += f4_dot(pv, lv); s0 += f4_dot(px, lv); s1 += f4_dot(py, lv); sv += f4_dot(pv, dl);
+        S[0] += f4_dot(a, lv); S[1] += f4_dot(bb, lv); S[2] += f4_dot(cc, lv); S[3] += f4_dot(d, lv);
+        R[0] += f4_dot(a, dl); R[1] += f4_dot(bb, dl); R[2] += f4_dot(cc, dl); R[3] += f4_dot(d, dl);
       }
+      const float wy0 = -b.dx_nw, wy1 = -b.dx_sw, wx0 = -b.dy_nw, wx1 = -b.dy_ne;
+      const float s = b.nw * S[0] + b.ne * S[1] + b.sw * S[2] + b.se * S[3];
+      const float s0 = wy0 * (S[1] - S[0]) + wy1 * (S[3] - S[2]);
+      const float s1 = wx0 * (S[2] - S[0]) + wx1 * (S[3] - S[1]);
+      const float sv = b.nw * R[0] + b.ne * R[1] + b.sw * R[2] + b.se * R[3];
       ft += s; gr[m0] += s0 * sx; gr[m1] += s1 * sy; gr[v] += sv * sl;
     }
     feat[i] = ft;

@@ -1,0 +1,70 @@
+"""Ray-batch data parallelism: one process per GPU, every rank runs the same model on its own
+slice of rays, and the parameter gradients are averaged with ONE all-reduce of a single flattened fp32 bucket
+per step (NCCL over NVLink 5 / NVSwitch; gloo in the CPU tests).  The reference itself has no data exchange
+(vestigial init_process_group + one barrier, train_tensoIR.py:21-27, utils.py:231-242).
+
+Everything else (regularisers, updateAlphaMask / shrink / upsample, Adam) is a deterministic function of the
+identical parameters and is simply replicated, so this is the only collective of the training path.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List
+
+import torch
+import torch.distributed as dist
+
+
+def _params_with_grad(params: Iterable[torch.nn.Parameter]) -> List[torch.nn.Parameter]:
+    return [p for p in params if p.requires_grad]
+
+
+class GradBucket:
+    """Persistent flat fp32 gradient bucket; ``p.grad`` of every parameter becomes a view into it, so the
+    all-reduce needs no per-step flatten / unflatten copies.  Rebuild after shrink / upsample (new Parameters)."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.params = _params_with_grad(params)
+        if not self.params:
+            raise ValueError("no parameters")
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        o = 0
+        self.views = []
+        for p in self.params:
+            v = self.flat[o:o + p.numel()].view_as(p)
+            self.views.append(v)
+            o += p.numel()
+
+    def numel(self):
+        return self.flat.numel()
+
+    def gather(self):
+        """Copy (or alias) the parameters' grads into the bucket; missing grads count as zero."""
+        for p, v in zip(self.params, self.views):
+            if p.grad is None:
+                v.zero_()
+            elif p.grad.data_ptr() != v.data_ptr():
+                v.copy_(p.grad)
+                p.grad = v
+
+    def all_reduce_mean(self, group=None):
+        self.gather()
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            self.flat.div_(dist.get_world_size(group))
+
+
+def shard_batch(n: int, rank: int, world: int):
+    """Contiguous slice [lo, hi) of an n-ray batch owned by ``rank`` (equal sizes; n must divide evenly so that
+    per-rank loss means average to the global mean)."""
+    if n % world:
+        raise ValueError(f"batch {n} not divisible by world size {world}")
+    per = n // world
+    return rank * per, (rank + 1) * per
+
+
+def broadcast_parameters(params: Iterable[torch.Tensor], src: int = 0, group=None):
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        for p in params:
+            dist.broadcast(p.data, src=src, group=group)

@@ -208,3 +208,39 @@ def app_mlp_points(model, xn, x_in, light_idx=None, *, head="renderModule", ligh
                                       None if li is None else _lib.dptr(li, torch.int32), n, act, _lib.dptr(out),
                                       _lib.stream_ptr()), "tir_app_mlp_points")
     return out
+
+
+class SecondaryStages:
+    """The two kernels of tir_secondary_radiance as separately launchable stages (bench / profiling):
+    ``march()`` = cosine test + density march + compaction, ``mlp()`` = appearance gather + MLP on the list."""
+
+    def __init__(self, model, surf_xyz, normals, light_idx, dirs, n_sample=96, near=0.05, far=1.5):
+        self.lib = _lib.load()
+        self.f = device_field(model).refresh(model)
+        self.keep = []
+        dev = surf_xyz.device
+        self.cfg = march_cfg(model, table=equal_z_table(n_sample, near, far, dev), keep=self.keep)
+        self.mlp_s = mlp_struct(model, "renderModule", self.keep, light="index")
+        self.sx, self.nr, self.dr = _f32c(surf_xyz.reshape(-1, 3)), _f32c(normals.reshape(-1, 3)), _f32c(dirs.reshape(-1, 3))
+        self.li = _i32c(light_idx)
+        self.n_pts, self.n_dirs = self.sx.shape[0], self.dr.shape[0]
+        self.vis = torch.zeros(self.n_pts, self.n_dirs, 1, device=dev)
+        self.ind = torch.zeros(self.n_pts, self.n_dirs, 3, device=dev)
+        self.sc = SampleScratch(dev, max(1 << 16, 4 * self.n_pts * self.n_dirs))
+        self.counters = new_counters(dev)
+
+    def march(self):
+        self.sc.count.zero_()
+        self.counters.zero_()
+        _lib.check(self.lib.tir_secondary_march(C.byref(self.f), _lib.dptr(self.sx), _lib.dptr(self.nr), self.n_pts,
+                                                _lib.dptr(self.dr), self.n_dirs, C.byref(self.cfg),
+                                                _lib.dptr(self.vis), _lib.dptr(self.sc.buf, torch.uint8),
+                                                _lib.dptr(self.sc.count, torch.int32), self.sc.capacity,
+                                                _lib.dptr(self.counters, torch.int64), _lib.stream_ptr()),
+                   "tir_secondary_march")
+
+    def mlp(self):
+        _lib.check(self.lib.tir_app_mlp(C.byref(self.f), C.byref(self.mlp_s), _lib.dptr(self.sc.buf, torch.uint8),
+                                        _lib.dptr(self.sc.count, torch.int32), self.sc.capacity, _lib.dptr(self.dr),
+                                        self.n_dirs, _lib.dptr(self.li, torch.int32), _lib.dptr(self.ind),
+                                        _lib.stream_ptr()), "tir_app_mlp")
