@@ -127,7 +127,7 @@ def workload_config(a, parallelism):
     return {"workload": f"relight training step, lego-shaped synthetic scene (BASELINE configs[1] shape): "
                         f"TensorVMSplit {a.grid}^3 (16/48 comps, 3 MLP heads, SG light), batch {a.batch} rays of "
                         f"100 views 800x800, N_samples {n_samples_for(a.grid)}, 16x32 stratified secondary dirs x 96 "
-                        f"samples, fwd+bwd+Adam", "global_batch_rays": a.batch * max(1, a.gpus),
+                        f"samples, fwd+bwd+Adam(fused)", "global_batch_rays": a.batch * max(1, a.gpus),
             "grid": a.grid, "parallelism": parallelism,
             "l2": "inputs change every step (new ray batch, updated parameters); VM tensors "
                   f"({'exceed' if a.grid >= 256 else 'fit in'} L2 at this grid)"}
@@ -194,7 +194,9 @@ def main():
     broadcast_parameters(model.parameters())
     params = [p for grp in model.get_optparam_groups(0.02, 0.001) for p in (grp["params"] if isinstance(
         grp["params"], (list, tuple, torch.nn.ParameterList)) else list(grp["params"]))]
-    opt = torch.optim.Adam(model.get_optparam_groups(0.02, 0.001), betas=(0.9, 0.99))
+    # same optimiser and hyper-parameters as train_tensoIR.py:206; fused=True selects PyTorch's single-kernel
+    # multi-tensor implementation of the identical update
+    opt = torch.optim.Adam(model.get_optparam_groups(0.02, 0.001), betas=(0.9, 0.99), fused=True)
     bucket = GradBucket(params) if world > 1 else None
     poses = hemisphere_poses(100)
     n_s = n_samples_for(a.grid)

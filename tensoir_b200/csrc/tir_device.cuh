@@ -20,6 +20,27 @@ __device__ __forceinline__ float unnormalize(float c, int size) {
   return __fmul_rn(__fmul_rn(__fadd_rn(c, 1.f), 0.5f), (float)(size - 1));
 }
 
+// floor() without the XU (FRND / F2I run at quarter rate on the conversion pipe and carry a long latency, which made
+// the march issue-latency bound): round-to-nearest via the 1.5*2^23 magic constant, then fix up.  Exact for |x| < 2^22
+// (grid coordinates are < 2^10); out-of-range inputs fall back to floorf so semantics never change.
+struct FloorI {
+  float f;
+  int i;
+};
+__device__ __forceinline__ FloorI floor_fi(float x) {
+  FloorI r;
+  if (fabsf(x) < 4194304.f) {
+    const float m = __fadd_rn(x, 12582912.f);
+    r.i = __float_as_int(m) - 0x4B400000;
+    r.f = __fsub_rn(m, 12582912.f);
+    if (r.f > x) { r.f = __fsub_rn(r.f, 1.f); r.i -= 1; }
+  } else {
+    r.f = floorf(x);
+    r.i = (int)r.f;
+  }
+  return r;
+}
+
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 struct Bilinear {
@@ -30,10 +51,11 @@ struct Bilinear {
 // F.grid_sample(bilinear, zeros, align_corners=True) tap set for one plane (W = grid[m0], H = grid[m1]).
 __device__ __forceinline__ Bilinear bilinear_setup(float gx, float gy, int W, int H) {
   float ix = unnormalize(gx, W), iy = unnormalize(gy, H);
-  float x0f = floorf(ix), y0f = floorf(iy);
+  const FloorI fx = floor_fi(ix), fy = floor_fi(iy);
+  float x0f = fx.f, y0f = fy.f;
   float wx1 = __fsub_rn(ix, x0f), wx0 = __fsub_rn(__fadd_rn(x0f, 1.f), ix);
   float wy1 = __fsub_rn(iy, y0f), wy0 = __fsub_rn(__fadd_rn(y0f, 1.f), iy);
-  int x0 = (int)x0f, y0 = (int)y0f, x1 = x0 + 1, y1 = y0 + 1;
+  int x0 = fx.i, y0 = fy.i, x1 = x0 + 1, y1 = y0 + 1;
   bool bx0 = (x0 >= 0) & (x0 < W), bx1 = (x1 >= 0) & (x1 < W);
   bool by0 = (y0 >= 0) & (y0 < H), by1 = (y1 >= 0) & (y1 < H);
   int cx0 = min(max(x0, 0), W - 1), cx1 = min(max(x1, 0), W - 1);
@@ -55,8 +77,9 @@ struct Linear1 {
 // The W=1 "line" case of the same sampler: x coordinate 0 -> ix = 0, taps nw (weight y1-iy) and sw (iy-y0).
 __device__ __forceinline__ Linear1 linear_setup(float gy, int D) {
   float iy = unnormalize(gy, D);
-  float y0f = floorf(iy);
-  int y0 = (int)y0f, y1 = y0 + 1;
+  const FloorI fy = floor_fi(iy);
+  float y0f = fy.f;
+  int y0 = fy.i, y1 = y0 + 1;
   Linear1 l;
   l.w0 = ((y0 >= 0) & (y0 < D)) ? __fsub_rn(__fadd_rn(y0f, 1.f), iy) : 0.f;
   l.w1 = ((y1 >= 0) & (y1 < D)) ? __fsub_rn(iy, y0f) : 0.f;
@@ -136,8 +159,9 @@ __device__ __forceinline__ bool alpha_mask_positive(const TirField& f, float px,
   float gy = __fsub_rn(__fmul_rn(__fsub_rn(py, f.a_lo[1]), f.a_inv[1]), 1.f);
   float gz = __fsub_rn(__fmul_rn(__fsub_rn(pz, f.a_lo[2]), f.a_inv[2]), 1.f);
   float ix = unnormalize(gx, X), iy = unnormalize(gy, Y), iz = unnormalize(gz, Z);
-  float x0f = floorf(ix), y0f = floorf(iy), z0f = floorf(iz);
-  int x0 = (int)x0f, y0 = (int)y0f, z0 = (int)z0f;
+  const FloorI ffx = floor_fi(ix), ffy = floor_fi(iy), ffz = floor_fi(iz);
+  float x0f = ffx.f, y0f = ffy.f, z0f = ffz.f;
+  int x0 = ffx.i, y0 = ffy.i, z0 = ffz.i;
   float fx1 = __fsub_rn(ix, x0f), fy1 = __fsub_rn(iy, y0f), fz1 = __fsub_rn(iz, z0f);
   const bool inside = (x0 >= 0) & (x0 < X) & (y0 >= 0) & (y0 < Y) & (z0 >= 0) & (z0 < Z);
   if (inside & (fx1 > 0.f) & (fy1 > 0.f) & (fz1 > 0.f)) {

@@ -13,6 +13,7 @@ namespace {
 
 constexpr int kWarpsPerBlock = 8;
 constexpr int kQueue = 64;
+constexpr int kBlocksPerSM = 3;
 
 struct QEntry {
   float x, y, z;   // normalised coords
@@ -41,7 +42,7 @@ struct MarchParams {
 };
 
 template <int C, int SAMPLING, bool WITH_APP, bool DENSE>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) march_kernel(const MarchParams p) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, kBlocksPerSM) march_kernel(const MarchParams p) {
   __shared__ QEntry queue[kWarpsPerBlock][kQueue];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -209,7 +210,7 @@ int launch_march(const MarchParams& p, cudaStream_t stream) {
   if (p.f.dC != 16) return TIR_ERR_SHAPE;
   if (p.cfg.n_samples <= 0) return TIR_ERR_CONFIG;
   int64_t blocks = (p.n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  const int64_t max_blocks = 148 * 8;   // persistent: 8 CTAs x 8 warps per SM
+  const int64_t max_blocks = 148 * kBlocksPerSM;   // persistent: every resident CTA slot of the 148 SMs, grid-stride over rays
   if (blocks > max_blocks) blocks = max_blocks;
   if (p.cfg.sampling == TIR_SAMPLE_STEP) {
     march_kernel<16, TIR_SAMPLE_STEP, WITH_APP, DENSE><<<(int)blocks, kWarpsPerBlock * 32, 0, stream>>>(p);

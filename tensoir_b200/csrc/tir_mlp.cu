@@ -3,10 +3,13 @@
 // Replaces compute_appfeature / compute_intrinfeature (tensoRF_rotated_lights.py:167-224) + MLPRender_Fea /
 // MLPBRDF_PEandFeature (tensorBase:122-146, :182-208).
 //
-// v1: fp32 SIMT.  Persistent CTAs keep all weights resident in shared memory (162 KB) and stream tiles of
-// 48 samples through two ping-pong activation buffers stored k-major ([k][sample]) so that the register-tiled
-// GEMM inner loops read 128-bit, conflict-free operands.  (1e-4 relative parity rules out plain TF32/BF16
-// tensor-core math; an error-compensated tcgen05 path is the planned replacement.)
+// The four contractions are genuine dense GEMMs over a tile of 64 samples and run on the tensor cores with
+// error-compensated BF16: every fp32 operand x is split into hi = bf16(x), lo = bf16(x - hi) and the product is
+// accumulated in fp32 as A_hi*B_hi + A_hi*B_lo + A_lo*B_hi (the dropped lo*lo term is 2^-16 relative), which keeps
+// the 1e-4 parity bar that plain BF16/TF32 (~1e-3) would miss.  Persistent CTAs (one per SM) keep all weights
+// resident in shared memory as split BF16 (176 KB) and stream 64-sample tiles through one in-place activation
+// buffer; fragments are fetched with ldmatrix from rows padded to an odd multiple of 16 bytes (conflict free).
+#include <cuda_bf16.h>
 #include "tir_device.cuh"
 
 using namespace tir;
@@ -14,27 +17,30 @@ using namespace tir;
 namespace {
 
 constexpr int AC = 48;            // appearance channels / orientation
-constexpr int K0 = 3 * AC;        // 144
+constexpr int K0 = 3 * AC;        // 144 = basis K (9 k16 steps)
 constexpr int F = 27;             // app_dim
-constexpr int FP = 28;            // padded
+constexpr int FN = 32;            // basis N padded
 constexpr int HID = 128;
 constexpr int IN = 150;           // 27 + 3 + 54 + 54 + 6 + 6
-constexpr int INP = 152;
-constexpr int M = 48;             // samples per tile
-constexpr int NT = 192;           // threads: (M/4) x (HID/8) register tiles of 4 x 8
+constexpr int K1 = 160;           // IN padded to k16
+constexpr int ON = 8;             // output N padded (<= 4 real)
+constexpr int M = 64;             // samples per tile
+constexpr int NT = 256;           // 8 warps
+constexpr int SA = 168;           // activation row stride (bf16 elements); 336 B = odd multiple of 16 B
+constexpr int SW0 = 168;          // W0 rows [128][K1 -> 168]
+constexpr int SW1 = 136;          // W1 rows [128][128 -> 136]
+constexpr int SBS = 152;          // basis rows [32][144 -> 152]
+constexpr int SW2 = 136;          // W2 rows [8][128 -> 136]
 
-struct SmemLayout {
-  float w0t[INP * HID];     // [k][h]
-  float w1t[HID * HID];     // [k][h]
-  float basist[K0 * FP];    // [k][f]
-  float w2t[HID * 4];       // [k][o]
-  float b0[HID];
-  float b1[HID];
-  float b2[4];
-  float bufA[INP * M];      // [k][m]
-  float bufB[K0 * M];       // [k][m]
+struct Smem {
+  __nv_bfloat16 w0h[HID * SW0], w0l[HID * SW0];
+  __nv_bfloat16 w1h[HID * SW1], w1l[HID * SW1];
+  __nv_bfloat16 bsh[FN * SBS], bsl[FN * SBS];
+  __nv_bfloat16 w2h[ON * SW2], w2l[ON * SW2];
+  __nv_bfloat16 ah[M * SA], al[M * SA];      // activations, in place across layers
+  float b0[HID], b1[HID], b2[ON];
   float xn[M][3];
-  float xv[M][3];           // view dir (radiance head) or position (BRDF / normal heads)
+  float xv[M][3];
   float wgt[M];
   int ray[M];
   int light[M];
@@ -43,7 +49,6 @@ struct SmemLayout {
 struct MlpParams {
   TirField f;
   TirMlp mlp;
-  // list source
   const TirAppSample* samples;
   const uint32_t* sample_count;
   int64_t max_samples;
@@ -51,7 +56,6 @@ struct MlpParams {
   int n_dirs;
   const int32_t* light_idx;
   float* rgb_out;
-  // point source
   const float* pts_xn;
   const float* pts_x;
   int64_t n_points;
@@ -59,33 +63,115 @@ struct MlpParams {
   int act;        // 0 sigmoid, 1 tanh
 };
 
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& h, __nv_bfloat16& l) {
+  h = __float2bfloat16_rn(x);
+  l = __float2bfloat16_rn(x - __bfloat162float(h));
+}
+
+__device__ __forceinline__ void store_pair(__nv_bfloat16* hi, __nv_bfloat16* lo, int idx, float a, float b) {
+  __nv_bfloat16 ah, al, bh, bl;
+  split_bf16(a, ah, al);
+  split_bf16(b, bh, bl);
+  __nv_bfloat162 vh, vl;
+  vh.x = ah; vh.y = bh; vl.x = al; vl.y = bl;
+  *reinterpret_cast<__nv_bfloat162*>(hi + idx) = vh;
+  *reinterpret_cast<__nv_bfloat162*>(lo + idx) = vl;
+}
+
+__device__ __forceinline__ void store_one(__nv_bfloat16* hi, __nv_bfloat16* lo, int idx, float a) {
+  __nv_bfloat16 h, l;
+  split_bf16(a, h, l);
+  hi[idx] = h;
+  lo[idx] = l;
+}
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const __nv_bfloat16* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+
+__device__ __forceinline__ void ldsm_x2(uint32_t (&r)[2], const __nv_bfloat16* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];\n" : "=r"(r[0]), "=r"(r[1]) : "r"(a));
+}
+
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// One warp: acc[MT][NTL] (m16 x n8 tiles) += A[m0.., :K] * W[n0.., :K]^T with the 3-term split.
+// A row-major [M][SA] (hi/lo), W row-major [N][SWx] (hi/lo) == PyTorch [out,in].
+template <int MT, int NTL>
+__device__ __forceinline__ void warp_gemm(float (&acc)[MT][NTL][4], const __nv_bfloat16* ah, const __nv_bfloat16* al,
+                                          int m0, const __nv_bfloat16* wh, const __nv_bfloat16* wl, int sw, int n0,
+                                          int K, int lane) {
+  // ldmatrix source rows: A x4 = {(r0-7,k0-7),(r8-15,k0-7),(r0-7,k8-15),(r8-15,k8-15)}
+  const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8;
+  const int a_col = (lane >> 4) * 8;
+  // B x4 (two n8 tiles) = {(n0-7,k0-7),(n0-7,k8-15),(n8-15,k0-7),(n8-15,k8-15)};  x2 (one tile) = first two
+  const int b_row = (lane & 7) + (lane >> 4) * 8;
+  const int b_col = ((lane >> 3) & 1) * 8;
+  for (int k = 0; k < K; k += 16) {
+    uint32_t bh[NTL][2], bl[NTL][2];
+    if (NTL == 2) {
+      uint32_t t[4];
+      ldsm_x4(t, wh + (n0 + b_row) * sw + k + b_col);
+      bh[0][0] = t[0]; bh[0][1] = t[1]; bh[NTL - 1][0] = t[2]; bh[NTL - 1][1] = t[3];
+      ldsm_x4(t, wl + (n0 + b_row) * sw + k + b_col);
+      bl[0][0] = t[0]; bl[0][1] = t[1]; bl[NTL - 1][0] = t[2]; bl[NTL - 1][1] = t[3];
+    } else {
+      uint32_t t[2];
+      ldsm_x2(t, wh + (n0 + (lane & 7)) * sw + k + b_col);
+      bh[0][0] = t[0]; bh[0][1] = t[1];
+      ldsm_x2(t, wl + (n0 + (lane & 7)) * sw + k + b_col);
+      bl[0][0] = t[0]; bl[0][1] = t[1];
+    }
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      uint32_t fh[4], fl[4];
+      ldsm_x4(fh, ah + (m0 + mt * 16 + a_row) * SA + k + a_col);
+      ldsm_x4(fl, al + (m0 + mt * 16 + a_row) * SA + k + a_col);
+#pragma unroll
+      for (int nt = 0; nt < NTL; ++nt) {
+        mma_bf16(acc[mt][nt], fl, bh[nt][0], bh[nt][1]);   // small terms first
+        mma_bf16(acc[mt][nt], fh, bl[nt][0], bl[nt][1]);
+        mma_bf16(acc[mt][nt], fh, bh[nt][0], bh[nt][1]);
+      }
+    }
+  }
+}
+
 template <bool POINTS>
 __global__ void __launch_bounds__(NT, 1) app_mlp_kernel(const MlpParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  SmemLayout& s = *reinterpret_cast<SmemLayout*>(smem_raw);
-  const int tid = threadIdx.x;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
   const TirMlp& mlp = p.mlp;
   const int out_dim = mlp.out_dim;
 
-  // ---- stage weights (transposed to k-major) once per CTA
-  for (int i = tid; i < INP * HID; i += NT) {
-    int k = i / HID, h = i % HID;
-    s.w0t[i] = (k < IN) ? __ldg(mlp.w0 + h * IN + k) : 0.f;
+  // ---- stage split-BF16 weights once per CTA (PyTorch [out,in] layout is already the mma "col" operand)
+  for (int i = tid; i < HID * SW0; i += NT) {
+    const int h = i / SW0, k = i % SW0;
+    split_bf16(k < IN ? __ldg(mlp.w0 + h * IN + k) : 0.f, s.w0h[i], s.w0l[i]);
   }
-  for (int i = tid; i < HID * HID; i += NT) {
-    int k = i / HID, h = i % HID;
-    s.w1t[i] = __ldg(mlp.w1 + h * HID + k);
+  for (int i = tid; i < HID * SW1; i += NT) {
+    const int h = i / SW1, k = i % SW1;
+    split_bf16(k < HID ? __ldg(mlp.w1 + h * HID + k) : 0.f, s.w1h[i], s.w1l[i]);
   }
-  for (int i = tid; i < K0 * FP; i += NT) {
-    int k = i / FP, ff = i % FP;
-    s.basist[i] = (ff < F) ? __ldg(mlp.basis + ff * K0 + k) : 0.f;
+  for (int i = tid; i < FN * SBS; i += NT) {
+    const int n = i / SBS, k = i % SBS;
+    split_bf16((n < F && k < K0) ? __ldg(mlp.basis + n * K0 + k) : 0.f, s.bsh[i], s.bsl[i]);
   }
-  for (int i = tid; i < HID * 4; i += NT) {
-    int k = i / 4, o = i % 4;
-    s.w2t[i] = (o < out_dim) ? __ldg(mlp.w2 + o * HID + k) : 0.f;
+  for (int i = tid; i < ON * SW2; i += NT) {
+    const int n = i / SW2, k = i % SW2;
+    split_bf16((n < out_dim && k < HID) ? __ldg(mlp.w2 + n * HID + k) : 0.f, s.w2h[i], s.w2l[i]);
   }
   for (int i = tid; i < HID; i += NT) { s.b0[i] = __ldg(mlp.b0 + i); s.b1[i] = __ldg(mlp.b1 + i); }
-  if (tid < 4) s.b2[tid] = (tid < out_dim) ? __ldg(mlp.b2 + tid) : 0.f;
+  if (tid < ON) s.b2[tid] = (tid < out_dim) ? __ldg(mlp.b2 + tid) : 0.f;
   __syncthreads();
 
   const int64_t total = POINTS ? p.n_points
@@ -119,7 +205,7 @@ __global__ void __launch_bounds__(NT, 1) app_mlp_kernel(const MlpParams p) {
     }
     __syncthreads();
 
-    // ---- phase 1: gather. 4 threads per sample, 12 channels of each orientation per thread -> bufB[k][m]
+    // ---- phase 1: gather.  4 threads per sample, 12 channels of each orientation per thread -> A[m][0..143]
     {
       const int m = tid >> 2, qd = tid & 3;
       const float xn[3] = {s.xn[m][0], s.xn[m][1], s.xn[m][2]};
@@ -137,108 +223,106 @@ __global__ void __launch_bounds__(NT, 1) app_mlp_kernel(const MlpParams p) {
           const float4 pv = bilerp4(ldg4(P + (size_t)b.o00 * AC + c), ldg4(P + (size_t)b.o01 * AC + c),
                                     ldg4(P + (size_t)b.o10 * AC + c), ldg4(P + (size_t)b.o11 * AC + c), b);
           const float4 lv = lerp4(ldg4(L + (size_t)l.o0 * AC + c), ldg4(L + (size_t)l.o1 * AC + c), l);
-          float4 lc = make_float4(1.f, 1.f, 1.f, 1.f);
-          if (lrow) lc = ldg4(lrow + k * AC + c);
-          const int kk = k * AC + c;
-          // (plane * line) * light  (tensoRF_rotated_lights.py:222)
-          s.bufB[(kk + 0) * M + m] = lrow ? __fmul_rn(__fmul_rn(pv.x, lv.x), lc.x) : __fmul_rn(pv.x, lv.x);
-          s.bufB[(kk + 1) * M + m] = lrow ? __fmul_rn(__fmul_rn(pv.y, lv.y), lc.y) : __fmul_rn(pv.y, lv.y);
-          s.bufB[(kk + 2) * M + m] = lrow ? __fmul_rn(__fmul_rn(pv.z, lv.z), lc.z) : __fmul_rn(pv.z, lv.z);
-          s.bufB[(kk + 3) * M + m] = lrow ? __fmul_rn(__fmul_rn(pv.w, lv.w), lc.w) : __fmul_rn(pv.w, lv.w);
+          float4 x = make_float4(__fmul_rn(pv.x, lv.x), __fmul_rn(pv.y, lv.y), __fmul_rn(pv.z, lv.z),
+                                 __fmul_rn(pv.w, lv.w));
+          if (lrow) {   // (plane * line) * light  (tensoRF_rotated_lights.py:222)
+            const float4 lc = ldg4(lrow + k * AC + c);
+            x.x = __fmul_rn(x.x, lc.x); x.y = __fmul_rn(x.y, lc.y); x.z = __fmul_rn(x.z, lc.z); x.w = __fmul_rn(x.w, lc.w);
+          }
+          const int col = k * AC + c;
+          store_pair(s.ah, s.al, m * SA + col, x.x, x.y);
+          store_pair(s.ah, s.al, m * SA + col + 2, x.z, x.w);
         }
       }
     }
     __syncthreads();
 
-    // ---- phase 2: basis_mat (144 -> 27) + MLP input assembly into bufA[k][m]
-    //      layout [feat 27 | x 3 | sin PE(feat) 54 | cos 54 | sin PE(x) 6 | cos 6]  (tensorBase:12-17, :136-142)
+    // ---- phase 2: basis_mat (144 -> 27, N padded to 32): warp w -> m-tile w/2, n-tiles 2*(w%2), +1
     {
-      const int m = tid % M, fg = tid / M;   // fg in 0..3, 7 features each
-      float a[7];
+      float acc[1][2][4] = {};
+      const int m0 = (warp >> 1) * 16, n0 = (warp & 1) * 16;
+      warp_gemm<1, 2>(acc, s.ah, s.al, m0, s.bsh, s.bsl, SBS, n0, K0, lane);
+      __syncthreads();   // every warp has finished reading the gathered products; A is rewritten in place
+      // MLP input [feat 27 | x 3 | sin PE(feat) 54 | cos 54 | sin PE(x) 6 | cos 6 | 0 pad 10]  (tensorBase:12-17,:136-142)
 #pragma unroll
-      for (int j = 0; j < 7; ++j) a[j] = 0.f;
-      for (int k = 0; k < K0; ++k) {
-        const float x = s.bufB[k * M + m];
-        const float* bw = s.basist + k * FP + fg * 7;
+      for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-        for (int j = 0; j < 7; ++j) a[j] = fmaf(x, bw[j], a[j]);
-      }
+        for (int half = 0; half < 2; ++half) {
+          const int row = m0 + g + half * 8;
+          const int n = n0 + nt * 8 + 2 * t4;
+          const float va = acc[0][nt][half * 2], vb = acc[0][nt][half * 2 + 1];
+          if (n + 1 < F) {
+            store_pair(s.ah, s.al, row * SA + n, va, vb);
+          } else if (n < F) {
+            store_one(s.ah, s.al, row * SA + n, va);
+          }
 #pragma unroll
-      for (int j = 0; j < 7; ++j) {
-        const int ff = fg * 7 + j;
-        if (ff < F) {
-          const float v = a[j];
-          s.bufA[ff * M + m] = v;
-          float s1, c1, s2, c2;
-          sincosf(v, &s1, &c1);
-          sincosf(__fmul_rn(v, 2.f), &s2, &c2);
-          s.bufA[(30 + 2 * ff) * M + m] = s1; s.bufA[(31 + 2 * ff) * M + m] = s2;
-          s.bufA[(84 + 2 * ff) * M + m] = c1; s.bufA[(85 + 2 * ff) * M + m] = c2;
+          for (int e = 0; e < 2; ++e) {
+            const int nn = n + e;
+            if (nn < F) {
+              const float v = e ? vb : va;
+              float s1, c1, s2, c2;
+              sincosf(v, &s1, &c1);
+              sincosf(__fmul_rn(v, 2.f), &s2, &c2);
+              store_pair(s.ah, s.al, row * SA + 30 + 2 * nn, s1, s2);
+              store_pair(s.ah, s.al, row * SA + 84 + 2 * nn, c1, c2);
+            }
+          }
         }
-      }
-      if (fg == 0) {
+      if (tid < M) {
+        const int row = tid;
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-          const float v = s.xv[m][d];
-          s.bufA[(27 + d) * M + m] = v;
+          const float v = s.xv[row][d];
+          store_one(s.ah, s.al, row * SA + 27 + d, v);
           float s1, c1, s2, c2;
           sincosf(v, &s1, &c1);
           sincosf(__fmul_rn(v, 2.f), &s2, &c2);
-          s.bufA[(138 + 2 * d) * M + m] = s1; s.bufA[(139 + 2 * d) * M + m] = s2;
-          s.bufA[(144 + 2 * d) * M + m] = c1; s.bufA[(145 + 2 * d) * M + m] = c2;
+          store_pair(s.ah, s.al, row * SA + 138 + 2 * d, s1, s2);
+          store_pair(s.ah, s.al, row * SA + 144 + 2 * d, c1, c2);
         }
-        s.bufA[150 * M + m] = 0.f; s.bufA[151 * M + m] = 0.f;
+#pragma unroll
+        for (int c = IN; c < K1; c += 2) store_pair(s.ah, s.al, row * SA + c, 0.f, 0.f);
       }
     }
     __syncthreads();
 
-    // ---- phases 3/4: two hidden layers, 4 samples x 8 units per thread
-    const int mg = tid % 12, hg = tid / 12;
-    auto layer = [&](const float* __restrict__ act, const float* __restrict__ wt, const float* __restrict__ bias,
-                     int K, float* __restrict__ outb) {
-      float accv[4][8];
+    // ---- phases 3/4: hidden layers.  warp w -> all 64 rows x units [16w, 16w+16)
+    auto hidden_layer = [&](const __nv_bfloat16* wh, const __nv_bfloat16* wl, int sw, const float* bias, int K) {
+      float acc[4][2][4] = {};
+      warp_gemm<4, 2>(acc, s.ah, s.al, 0, wh, wl, sw, warp * 16, K, lane);
+      __syncthreads();
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) accv[i][j] = 0.f;
-#pragma unroll 2
-      for (int k = 0; k < K; ++k) {
-        const float4 av = *reinterpret_cast<const float4*>(act + k * M + mg * 4);
-        const float4 wa = *reinterpret_cast<const float4*>(wt + k * HID + hg * 8);
-        const float4 wb = *reinterpret_cast<const float4*>(wt + k * HID + hg * 8 + 4);
-        const float a4[4] = {av.x, av.y, av.z, av.w};
-        const float w8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) accv[i][j] = fmaf(a4[i], w8[j], accv[i][j]);
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float bj = bias[hg * 8 + j];
-        float4 o;
-        o.x = fmaxf(accv[0][j] + bj, 0.f); o.y = fmaxf(accv[1][j] + bj, 0.f);
-        o.z = fmaxf(accv[2][j] + bj, 0.f); o.w = fmaxf(accv[3][j] + bj, 0.f);
-        *reinterpret_cast<float4*>(outb + (hg * 8 + j) * M + mg * 4) = o;
-      }
+        for (int nt = 0; nt < 2; ++nt) {
+          const int n = warp * 16 + nt * 8 + 2 * t4;
+          const float ba = bias[n], bb = bias[n + 1];
+          store_pair(s.ah, s.al, (mt * 16 + g) * SA + n, fmaxf(acc[mt][nt][0] + ba, 0.f), fmaxf(acc[mt][nt][1] + bb, 0.f));
+          store_pair(s.ah, s.al, (mt * 16 + g + 8) * SA + n, fmaxf(acc[mt][nt][2] + ba, 0.f),
+                     fmaxf(acc[mt][nt][3] + bb, 0.f));
+        }
+      __syncthreads();
     };
-    layer(s.bufA, s.w0t, s.b0, INP, s.bufB);
-    __syncthreads();
-    layer(s.bufB, s.w1t, s.b1, HID, s.bufA);
-    __syncthreads();
+    hidden_layer(s.w0h, s.w0l, SW0, s.b0, K1);
+    hidden_layer(s.w1h, s.w1l, SW1, s.b1, HID);
 
-    // ---- phase 5: output layer + activation + composite
-    if (tid < M * 4) {
-      const int m = tid % M, o = tid / M;
-      if (o < out_dim) {
-        float a = 0.f;
-        for (int k = 0; k < HID; ++k) a = fmaf(s.bufA[k * M + m], s.w2t[k * 4 + o], a);
-        a += s.b2[o];
-        const float y = p.act == 0 ? 1.f / (1.f + expf(-a)) : tanhf(a);
-        const int64_t i = base + m;
-        if (i < total) {
-          if (POINTS) p.out[i * out_dim + o] = y;
-          else atomicAdd(p.rgb_out + (int64_t)s.ray[m] * 3 + o, __fmul_rn(s.wgt[m], y));
+    // ---- phase 5: output layer (N padded to 8) on warps 0..3, activation, composite
+    if (warp < 4) {
+      float acc[1][1][4] = {};
+      warp_gemm<1, 1>(acc, s.ah, s.al, warp * 16, s.w2h, s.w2l, SW2, 0, HID, lane);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int row = warp * 16 + g + (e >> 1) * 8;
+        const int o = 2 * t4 + (e & 1);
+        if (o < out_dim) {
+          const float a = acc[0][0][e] + s.b2[o];
+          const float y = p.act == 0 ? 1.f / (1.f + expf(-a)) : tanhf(a);
+          const int64_t i = base + row;
+          if (i < total) {
+            if (POINTS) p.out[i * out_dim + o] = y;
+            else atomicAdd(p.rgb_out + (int64_t)s.ray[row] * 3 + o, __fmul_rn(s.wgt[row], y));
+          }
         }
       }
     }
@@ -257,7 +341,7 @@ int check_shapes(const TirField* f, const TirMlp* m) {
 template <bool POINTS>
 int launch(const MlpParams& p, int64_t max_items, cudaStream_t stream) {
   static bool configured[2] = {false, false};
-  const int smem = (int)sizeof(SmemLayout);
+  const int smem = (int)sizeof(Smem);
   if (!configured[POINTS]) {
     cudaError_t e = cudaFuncSetAttribute(app_mlp_kernel<POINTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;

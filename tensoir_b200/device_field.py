@@ -59,9 +59,8 @@ class DeviceField:
                 raise _lib.TirError("kernels need equal channel counts across the three orientations")
             s.dC, s.aC = dcs.pop(), acs.pop()
             self._vm_key = key
-        gs = [int(g) for g in model.gridSize.tolist()]
-        lo, hi = model.aabb[0].tolist(), model.aabb[1].tolist()
-        inv = model.invaabbSize.tolist()
+        hg = model._host_geom
+        gs, lo, hi, inv = hg["grid"], hg["lo"], hg["hi"], hg["inv"]
         for i in range(3):
             s.grid[i] = gs[i]
             s.aabb_lo[i], s.aabb_hi[i], s.inv_aabb[i] = lo[i], hi[i], inv[i]
@@ -85,7 +84,7 @@ class DeviceField:
             Z, Y, X = vol.shape[-3:]
             s.amask, s.acell = self.amask.data_ptr(), self.acell.data_ptr()
             s.agrid[0], s.agrid[1], s.agrid[2] = X, Y, Z
-            alo, ainv = am.aabb[0].tolist(), am.invgridSize.tolist()
+            alo, ainv = am._host_geom["lo"], am._host_geom["inv"]
             for i in range(3):
                 s.a_lo[i], s.a_inv[i] = alo[i], ainv[i]
         s.density_shift = float(model.density_shift)

@@ -52,7 +52,7 @@ def march_cfg(model, *, table: Optional[torch.Tensor] = None, n_samples: int = -
     else:
         cfg.sampling = _lib.SAMPLE_STEP
         cfg.n_samples = int(n_samples if n_samples > 0 else model.nSamples)
-        cfg.step = float(model.stepSize)
+        cfg.step = model._host_geom["step"]
         cfg.near, cfg.far = float(model.near_far[0]), float(model.near_far[1])
         cfg.z_table = None
         if jitter is not None:

@@ -81,6 +81,7 @@ class AlphaGridMask(torch.nn.Module):
         self.alpha_volume = alpha_volume.view(1, 1, *alpha_volume.shape[-3:])
         self.gridSize = torch.LongTensor([alpha_volume.shape[-1], alpha_volume.shape[-2],
                                           alpha_volume.shape[-3]]).to(self.device)
+        self._host_geom = {"lo": self.aabb[0].tolist(), "inv": self.invgridSize.tolist()}
 
     def sample_alpha(self, xyz_sampled):
         """Trilinear lookup; on CUDA the >0 test of callers is served by tir_alpha_mask_points, this
@@ -284,6 +285,11 @@ class TensorBase(torch.nn.Module):
         self.stepSize = torch.mean(self.units) * self.step_ratio
         self.aabbDiag = torch.sqrt(torch.sum(torch.square(self.aabbSize)))
         self.nSamples = int((self.aabbDiag / self.stepSize).item()) + 1
+        # host copies of the (device-resident) geometry so that kernel launches never sync on .tolist()/.item();
+        # every path that changes aabb / gridSize (constructor, shrink, upsample) ends in update_stepSize
+        self._host_geom = {"grid": [int(g) for g in self.gridSize.tolist()], "lo": self.aabb[0].tolist(),
+                           "hi": self.aabb[1].tolist(), "inv": self.invaabbSize.tolist(),
+                           "step": float(self.stepSize)}
 
     def normalize_coord(self, xyz_sampled):
         return (xyz_sampled - self.aabb[0]) * self.invaabbSize - 1

@@ -48,9 +48,9 @@ def test_unit_kernels(rot):
     close(m.compute_appfeature(xn, li), fx["app_feat"], 2e-5)
     close(m.compute_intrinfeature(xn), fx["intrin_only"], 2e-5)
     vd = fx["viewdirs"].to(DEV)
-    close(ops.app_mlp_points(m, xn, vd, li, head="renderModule"), fx["mlp_rgb"], 2e-5, "mlp_rgb")
-    close(ops.app_mlp_points(m, xn, xn, None, head="renderModule_brdf", light="mean"), fx["mlp_brdf"], 2e-5, "brdf")
-    close(ops.app_mlp_points(m, xn, xn, None, head="renderModule_normal", light="mean"), fx["mlp_normal"], 2e-5, "nrm")
+    close(ops.app_mlp_points(m, xn, vd, li, head="renderModule"), fx["mlp_rgb"], 5e-5, "mlp_rgb")
+    close(ops.app_mlp_points(m, xn, xn, None, head="renderModule_brdf", light="mean"), fx["mlp_brdf"], 5e-5, "brdf")
+    close(ops.app_mlp_points(m, xn, xn, None, head="renderModule_normal", light="mean"), fx["mlp_normal"], 5e-5, "nrm")
     # derived normals: compare the raw gradient (absolute, vs its scale) and the unit normals where the gradient
     # is well conditioned (a normalised ~0 gradient amplifies summation-order noise by up to 1e6)
     from tensoir_b200.primary import _derived_normals
