@@ -21,7 +21,7 @@ from tensoir_b200.synthetic import make_lego_model, hemisphere_poses, training_b
 
 dev = torch.device("cuda:0")
 model = make_lego_model(a.grid, dev)
-opt = torch.optim.Adam(model.get_optparam_groups(0.02, 0.001), betas=(0.9, 0.99))
+opt = torch.optim.Adam(model.get_optparam_groups(0.02, 0.001), betas=(0.9, 0.99), fused=True)
 poses = hemisphere_poses(100)
 n_s = n_samples_for(a.grid)
 target = torch.full((4096, 3), 0.5, device=dev)
@@ -50,4 +50,5 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for b in batches[3:]:
         step(*b)
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=60))
+print(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=40, max_name_column_width=60))
