@@ -37,6 +37,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--cpu-rays", type=int, default=1024, help="bounded CPU-baseline sample (primary rays / step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="do not capture the step into a CUDA graph")
     return ap.parse_args()
 
 
@@ -192,11 +193,14 @@ def main():
 
     model = make_lego_model(a.grid, dev)
     broadcast_parameters(model.parameters())
-    params = [p for grp in model.get_optparam_groups(0.02, 0.001) for p in (grp["params"] if isinstance(
-        grp["params"], (list, tuple, torch.nn.ParameterList)) else list(grp["params"]))]
+    params = []
+    for grp in model.get_optparam_groups(0.02, 0.001):
+        gp = grp["params"]
+        params += [gp] if isinstance(gp, torch.Tensor) else list(gp)     # a bare Parameter must not be iterated
     # same optimiser and hyper-parameters as train_tensoIR.py:206; fused=True selects PyTorch's single-kernel
     # multi-tensor implementation of the identical update
-    opt = torch.optim.Adam(model.get_optparam_groups(0.02, 0.001), betas=(0.9, 0.99), fused=True)
+    opt = torch.optim.Adam(model.get_optparam_groups(0.02, 0.001), betas=(0.9, 0.99), fused=True,
+                           capturable=not a.eager)
     bucket = GradBucket(params) if world > 1 else None
     poses = hemisphere_poses(100)
     n_s = n_samples_for(a.grid)
@@ -208,7 +212,18 @@ def main():
     counters = ops.new_counters(dev)
     model.__dict__["_tir_counters"] = counters
 
+    graphed = None
+    if not a.eager:
+        # whole-step CUDA graph: static-capacity sample lists, host randoms staged into device buffers, replay
+        from tensoir_b200.static_step import StaticTrainStep
+        graphed = StaticTrainStep(model, opt, a.batch, n_s, Args, lambda ret, m: loss_of(ret, target, m),
+                                  grad_bucket=bucket, device=dev)
+        caps = graphed.calibrate(host_batches[:3])
+        graphed.capture(warmup=3)
+
     def step(rays, li):
+        if graphed is not None:
+            return graphed.run(rays, li)
         ret = Renderer_TensoIR_train(rays, None, li, model, N_samples=n_s, white_bg=True, is_train=True,
                                      is_relight=True, sample_method='stratified_sampling', chunk_size=160000,
                                      device=dev, args=Args)
@@ -265,6 +280,9 @@ def main():
     ms_e2e, cnt_e2e, _ = timed_region(pinned[total + a.warmup:2 * total], read_loss=True)
     clk = clocks.stop() if rank == 0 else None
     e2e_value = cnt_e2e["rays"] / (ms_e2e * 1e-3)
+    overflow = graphed.overflowed() if graphed is not None else 0
+    if graphed is not None:
+        graphed.release()
 
     if rank != 0:
         if world > 1:
@@ -281,7 +299,9 @@ def main():
             "counters_per_step": {k: v / a.steps for k, v in cnt.items()},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
                     "h2d_bytes_per_step": a.batch * (6 * 4 + 4) * world, "d2h_bytes_per_step": 4 * world},
-            "gpu_launches": launches, "clocks": clk, "roofline": roof}
+            "gpu_launches": launches, "clocks": clk, "roofline": roof,
+            "execution": ("eager" if a.eager else f"cuda-graph replay of the whole step (static list capacities "
+                          f"{caps}, overflowed steps: {overflow})")}
     if not a.no_cpu_baseline and world == 1:
         cb = cpu_baseline(a, steps=2, warmup=1)
         line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": "port",

@@ -215,15 +215,17 @@ int tir_valid_samples_count(const TirField* field, const float* rays_o, const fl
                             const TirMarchCfg* cfg, int32_t* counts, uint64_t* counters, void* stream);
 int tir_valid_samples_fill(const TirField* field, const float* rays_o, const float* rays_d, int64_t n_rays,
                            const TirMarchCfg* cfg, const int64_t* offsets, int32_t* out_ray, int32_t* out_sample,
-                           float* out_xn, float* out_z, float* out_dist, void* stream);
+                           float* out_xn, float* out_z, float* out_dist, int64_t capacity /* 0 = unbounded; rows past
+                           it are dropped (static-capacity lists for CUDA-graph capture) */, void* stream);
 
 /* raw2alpha (tensorBase:21-28) over ray segments of a valid-sample list, sequential like torch.cumprod:
  * weight[i] = alpha_i * T_i, trans[i] = T_i (exclusive), t_last[ray]. */
 int tir_composite_fwd(const float* sigma, const float* dist, const int64_t* offsets, int64_t n_rays,
-                      float distance_scale, float* weight, float* trans, float* t_last, void* stream);
+                      float distance_scale, float* weight, float* trans, float* t_last,
+                      int64_t limit /* 0 = none; list rows >= limit are ignored */, void* stream);
 int tir_composite_bwd(const float* sigma, const float* dist, const int64_t* offsets, int64_t n_rays,
                       float distance_scale, const float* weight, const float* trans, const float* g_weight,
-                      float* g_sigma, void* stream);
+                      float* g_sigma, int64_t limit, void* stream);
 
 #ifdef __cplusplus
 }

@@ -264,7 +264,7 @@ __global__ void valid_samples_kernel(TirField f, TirMarchCfg cfg, const float* _
                                      const int64_t* __restrict__ offsets, int32_t* __restrict__ out_ray,
                                      int32_t* __restrict__ out_sample, float* __restrict__ out_xn,
                                      float* __restrict__ out_z, float* __restrict__ out_dist,
-                                     unsigned long long* counters) {
+                                     unsigned long long* counters, int64_t capacity) {
   const int lane = threadIdx.x & 31;
   const int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (ray >= n_rays) return;
@@ -307,7 +307,7 @@ __global__ void valid_samples_kernel(TirField f, TirMarchCfg cfg, const float* _
       }
     }
     const unsigned m = __ballot_sync(0xffffffffu, valid);
-    if (FILL && valid) {
+    if (FILL && valid && (pos + __popc(m & ((1u << lane) - 1u)) < capacity)) {
       const int64_t o = pos + __popc(m & ((1u << lane) - 1u));
       out_ray[o] = (int32_t)ray; out_sample[o] = s;
       out_xn[o * 3] = nx; out_xn[o * 3 + 1] = ny; out_xn[o * 3 + 2] = nz;
@@ -332,11 +332,12 @@ __global__ void valid_samples_kernel(TirField f, TirMarchCfg cfg, const float* _
 __global__ void composite_fwd_kernel(const float* __restrict__ sigma, const float* __restrict__ dist,
                                      const int64_t* __restrict__ offsets, int64_t n_rays, float scale,
                                      float* __restrict__ weight, float* __restrict__ trans,
-                                     float* __restrict__ t_last) {
+                                     float* __restrict__ t_last, int64_t limit) {
   const int64_t ray = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (ray >= n_rays) return;
   float T = 1.f;
-  for (int64_t i = offsets[ray]; i < offsets[ray + 1]; ++i) {
+  const int64_t e_ = offsets[ray + 1] < limit ? offsets[ray + 1] : limit;
+  for (int64_t i = offsets[ray]; i < e_; ++i) {
     const float alpha = __fsub_rn(1.f, expf(__fmul_rn(-sigma[i], __fmul_rn(dist[i], scale))));
     weight[i] = __fmul_rn(alpha, T);
     trans[i] = T;
@@ -348,10 +349,11 @@ __global__ void composite_fwd_kernel(const float* __restrict__ sigma, const floa
 __global__ void composite_bwd_kernel(const float* __restrict__ sigma, const float* __restrict__ dist,
                                      const int64_t* __restrict__ offsets, int64_t n_rays, float scale,
                                      const float* __restrict__ weight, const float* __restrict__ trans,
-                                     const float* __restrict__ g_weight, float* __restrict__ g_sigma) {
+                                     const float* __restrict__ g_weight, float* __restrict__ g_sigma,
+                                     int64_t limit) {
   const int64_t ray = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (ray >= n_rays) return;
-  const int64_t b = offsets[ray], e = offsets[ray + 1];
+  const int64_t b = offsets[ray], e = offsets[ray + 1] < limit ? offsets[ray + 1] : limit;
   float suffix = 0.f;   // sum_{j>i} g_j * w_j
   for (int64_t i = e - 1; i >= b; --i) {
     const float d = dist[i] * scale;
@@ -433,39 +435,42 @@ extern "C" int tir_valid_samples_count(const TirField* field, const float* rays_
   const int64_t blocks = (n_rays * 32 + threads - 1) / threads;
   valid_samples_kernel<false><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
       *field, *cfg, rays_o, rays_d, n_rays, counts, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-      (unsigned long long*)counters);
+      (unsigned long long*)counters, 0);
   return (int)cudaGetLastError();
 }
 
 extern "C" int tir_valid_samples_fill(const TirField* field, const float* rays_o, const float* rays_d,
                                       int64_t n_rays, const TirMarchCfg* cfg, const int64_t* offsets,
                                       int32_t* out_ray, int32_t* out_sample, float* out_xn, float* out_z,
-                                      float* out_dist, void* stream) {
+                                      float* out_dist, int64_t capacity, void* stream) {
   if (!field || !rays_o || !rays_d || !cfg || !offsets || !out_ray || !out_sample || !out_xn || !out_z || !out_dist)
     return TIR_ERR_NULL;
   if (n_rays <= 0) return TIR_OK;
   const int threads = 256;
   const int64_t blocks = (n_rays * 32 + threads - 1) / threads;
   valid_samples_kernel<true><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
-      *field, *cfg, rays_o, rays_d, n_rays, nullptr, offsets, out_ray, out_sample, out_xn, out_z, out_dist, nullptr);
+      *field, *cfg, rays_o, rays_d, n_rays, nullptr, offsets, out_ray, out_sample, out_xn, out_z, out_dist, nullptr,
+      capacity > 0 ? capacity : (int64_t)1 << 62);
   return (int)cudaGetLastError();
 }
 
 extern "C" int tir_composite_fwd(const float* sigma, const float* dist, const int64_t* offsets, int64_t n_rays,
-                                 float distance_scale, float* weight, float* trans, float* t_last, void* stream) {
+                                 float distance_scale, float* weight, float* trans, float* t_last, int64_t limit,
+                                 void* stream) {
   if (!sigma || !dist || !offsets || !weight || !trans) return TIR_ERR_NULL;
   if (n_rays <= 0) return TIR_OK;
   composite_fwd_kernel<<<(unsigned)((n_rays + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-      sigma, dist, offsets, n_rays, distance_scale, weight, trans, t_last);
+      sigma, dist, offsets, n_rays, distance_scale, weight, trans, t_last, limit > 0 ? limit : (int64_t)1 << 62);
   return (int)cudaGetLastError();
 }
 
 extern "C" int tir_composite_bwd(const float* sigma, const float* dist, const int64_t* offsets, int64_t n_rays,
                                  float distance_scale, const float* weight, const float* trans,
-                                 const float* g_weight, float* g_sigma, void* stream) {
+                                 const float* g_weight, float* g_sigma, int64_t limit, void* stream) {
   if (!sigma || !dist || !offsets || !weight || !trans || !g_weight || !g_sigma) return TIR_ERR_NULL;
   if (n_rays <= 0) return TIR_OK;
   composite_bwd_kernel<<<(unsigned)((n_rays + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-      sigma, dist, offsets, n_rays, distance_scale, weight, trans, g_weight, g_sigma);
+      sigma, dist, offsets, n_rays, distance_scale, weight, trans, g_weight, g_sigma,
+      limit > 0 ? limit : (int64_t)1 << 62);
   return (int)cudaGetLastError();
 }

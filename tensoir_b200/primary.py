@@ -51,11 +51,18 @@ def _derived_normals(model, xn):
 def march(model, rays, is_train, n_samples, counters=None):
     """Shared front half: valid list -> sigma -> weights.  Returns a dict."""
     n_rays = rays.shape[0]
+    st = model.__dict__.get("_tir_static")       # shape-static mode (CUDA-graph capture), see static_step.py
     jitter = None
     if is_train:
-        # the reference draws the per-ray jitter on the CPU (rand_like of a CPU tensor, tensorBase:714-718)
-        jitter = torch.rand(n_rays, 1).to(rays.device)
-    lst = vm.valid_samples(model, rays[:, :3], rays[:, 3:6], n_samples=n_samples, jitter=jitter, counters=counters)
+        if st is not None:
+            jitter = st["jitter"]                # device buffer refilled by the host before every replay
+        else:
+            # the reference draws the per-ray jitter on the CPU (rand_like of a CPU tensor, tensorBase:714-718)
+            jitter = torch.rand(n_rays, 1).to(rays.device)
+    lst = vm.valid_samples(model, rays[:, :3], rays[:, 3:6], n_samples=n_samples, jitter=jitter, counters=counters,
+                           capacity=None if st is None else st["cap_valid"])
+    if st is not None:
+        st["overflow"] += lst["overflow"].to(st["overflow"].dtype)
     ray_id = lst["ray"].long()
     if lst["xn"].shape[0] > 0:
         feat = vm.density_feature(model, lst["xn"])
@@ -75,12 +82,26 @@ def forward_relight(model, rays_chunk, light_idx, white_bg=True, is_train=False,
     m = march(model, rays, is_train, N_samples, counters=model.__dict__.get("_tir_counters"))
     ray_id, weight, xn = m["ray_id"], m["weight"], m["xn"]
 
-    app_idx = torch.nonzero(weight > model.rayMarch_weight_thres).reshape(-1)
-    n_app = app_idx.shape[0]
+    st = model.__dict__.get("_tir_static")
     cnt = model.__dict__.get("_tir_counters")
-    if cnt is not None:
-        cnt[2] += n_app
-    w_a = weight[app_idx]
+    app_sel = weight > model.rayMarch_weight_thres
+    if st is None:
+        app_idx = torch.nonzero(app_sel).reshape(-1)
+        n_app = app_idx.shape[0]
+        if cnt is not None:
+            cnt[2] += n_app
+        w_a = weight[app_idx]
+    else:
+        # static capacity: padded index list, padding rows carry weight 0 (and therefore no gradient)
+        app_idx = torch.nonzero_static(app_sel, size=st["cap_app"], fill_value=-1).reshape(-1)
+        real = app_idx >= 0
+        app_idx = app_idx.clamp(min=0)
+        n_app = st["cap_app"]
+        n_real = app_sel.sum()
+        st["overflow"] += (n_real > st["cap_app"]).to(st["overflow"].dtype)
+        if cnt is not None:
+            cnt[2] += n_real
+        w_a = weight[app_idx] * real.to(weight.dtype)
     r_a = ray_id[app_idx]
     x_a = xn[app_idx]
 
@@ -142,7 +163,9 @@ def forward_relight(model, rays_chunk, light_idx, white_bg=True, is_train=False,
     if bg():
         depth_map = depth_map + (1. - acc_map) * rays[..., -1]
         rgb_map = rgb_map + (1. - acc_map[..., None])
-        normal_map = normal_map + (1 - acc_map[..., None]) * torch.tensor([0.0, 0.0, 1.0], device=dev)
+        # background normal (0, 0, 1), built from device-side fills only (CUDA-graph capturable)
+        bg_normal = torch.cat([torch.zeros(2, device=dev), torch.ones(1, device=dev)])
+        normal_map = normal_map + (1 - acc_map[..., None]) * bg_normal
         albedo_map = albedo_map + (1 - acc_map[..., None])
         roughness_map = roughness_map + (1 - acc_map[..., None])
         fresnel_map = fresnel_map + (1 - acc_map[..., None])

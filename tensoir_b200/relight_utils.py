@@ -91,8 +91,15 @@ def render_with_BRDF(depth_map, normal_map, albedo_map, roughness_map, fresnel_m
     device = depth_map.device
     rays_o, rays_d = rays[..., :3].to(device), rays[..., 3:].to(device)
     surface_xyz = rays_o + depth_map.unsqueeze(-1) * rays_d
-    light_area_weight = tensoIR.light_area_weight.to(device)
-    incident_light_dirs = tensoIR.gen_light_incident_dirs(method=sample_method).to(device)   # host draws, ref order
+    light_area_weight = tensoIR.__dict__.get("_tir_area_weight_dev")
+    if light_area_weight is None or light_area_weight.device != device:
+        light_area_weight = tensoIR.light_area_weight.to(device)
+        tensoIR.__dict__["_tir_area_weight_dev"] = light_area_weight
+    st = tensoIR.__dict__.get("_tir_static")
+    if st is not None:
+        incident_light_dirs = st["dirs"]         # device buffer refilled by the host (same generator order)
+    else:
+        incident_light_dirs = tensoIR.gen_light_incident_dirs(method=sample_method).to(device)   # host draws, ref order
     bs, nlights = surface_xyz.shape[0], incident_light_dirs.shape[0]
     surf2c = safe_l2_normalize(-rays_d, dim=-1)
     surf2l = incident_light_dirs.reshape(1, -1, 3).expand(bs, -1, -1)

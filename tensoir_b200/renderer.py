@@ -20,7 +20,15 @@ def Renderer_TensoIR_train(rays=None, normal_gt=None, light_idx=None, tensoIR=No
                 N_samples=N_samples)
     if tensoIR.normals_kind == "gt_normals" and normal_gt is not None:
         normal_map = normal_gt.to(device)
-    if is_relight:
+    if is_relight and tensoIR.__dict__.get("_tir_static") is not None:
+        # shape-static variant (CUDA-graph capture): no compaction of the acc_mask rows.  Rays that miss get a zero
+        # normal for the secondary kernel (its cosine test then skips all their directions) and their shaded value
+        # is replaced by the white background afterwards, exactly as the scatter below does.
+        keep = acc_mask[:, None].to(normal_map.dtype)
+        shaded = render_with_BRDF(depth_map, normal_map * keep, albedo_map, roughness_map.repeat(1, 3), fresnel_map, rays, tensoIR, light_idx,
+                                  sample_method, chunk_size=chunk_size, device=device, args=args)
+        rgb_with_brdf = torch.where(acc_mask[:, None], shaded, torch.ones_like(rgb_map))
+    elif is_relight:
         masked = render_with_BRDF(depth_map[acc_mask], normal_map[acc_mask], albedo_map[acc_mask],
                                   roughness_map[acc_mask].repeat(1, 3), fresnel_map[acc_mask], rays[acc_mask],
                                   tensoIR, light_idx[acc_mask], sample_method, chunk_size=chunk_size,

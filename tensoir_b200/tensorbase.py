@@ -21,7 +21,7 @@ from . import primary
 
 def positional_encoding(positions, freqs):
     """tensorBase_rotated_lights.py:12-17 (index layout d*F+f, [sin | cos])."""
-    freq_bands = (2 ** torch.arange(freqs).float()).to(positions.device)
+    freq_bands = 2 ** torch.arange(freqs, device=positions.device).float()
     pts = (positions[..., None] * freq_bands).reshape(positions.shape[:-1] + (freqs * positions.shape[-1],))
     return torch.cat([torch.sin(pts), torch.cos(pts)], dim=-1)
 
@@ -239,7 +239,7 @@ class TensorBase(torch.nn.Module):
                 a = torch.tensor(self.light_rotation[i] / 180 * torch.pi).to(torch.float32)
                 mats.append(torch.tensor([[torch.cos(a), -torch.sin(a), 0], [torch.sin(a), torch.cos(a), 0],
                                           [0, 0, 1]]).to(torch.float32))
-            self.light_rotation_matrix = torch.stack(mats, dim=0)
+            self.light_rotation_matrix = torch.stack(mats, dim=0).to(self.device)
 
     def gen_light_incident_dirs(self, sample_number=-1, method='fixed_envirmap', device='cuda'):
         """tensorBase_rotated_lights.py:492-574.  Draws stay on the host in the reference's order."""

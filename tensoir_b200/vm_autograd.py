@@ -156,12 +156,12 @@ class _Composite(torch.autograd.Function):
         lib = _lib.load()
         sigma = sigma.contiguous()
         n_rays = offsets.numel() - 1
-        weight = torch.empty_like(sigma)
-        trans = torch.empty_like(sigma)
+        weight = torch.zeros_like(sigma)      # rows of a static-capacity list past the real total stay 0
+        trans = torch.zeros_like(sigma)
         t_last = torch.empty(n_rays, device=sigma.device)
         _lib.check(lib.tir_composite_fwd(_lib.dptr(sigma), _lib.dptr(dist), _lib.dptr(offsets, torch.int64), n_rays,
                                          float(scale), _lib.dptr(weight), _lib.dptr(trans), _lib.dptr(t_last),
-                                         _lib.stream_ptr()), "tir_composite_fwd")
+                                         sigma.numel(), _lib.stream_ptr()), "tir_composite_fwd")
         ctx.save_for_backward(sigma, dist, offsets, weight, trans)
         ctx.scale = float(scale)
         ctx.mark_non_differentiable(t_last)
@@ -172,10 +172,10 @@ class _Composite(torch.autograd.Function):
         sigma, dist, offsets, weight, trans = ctx.saved_tensors
         lib = _lib.load()
         g_weight = g_weight.contiguous().float()
-        g_sigma = torch.empty_like(sigma)
+        g_sigma = torch.zeros_like(sigma)
         _lib.check(lib.tir_composite_bwd(_lib.dptr(sigma), _lib.dptr(dist), _lib.dptr(offsets, torch.int64),
                                          offsets.numel() - 1, ctx.scale, _lib.dptr(weight), _lib.dptr(trans),
-                                         _lib.dptr(g_weight), _lib.dptr(g_sigma), _lib.stream_ptr()),
+                                         _lib.dptr(g_weight), _lib.dptr(g_sigma), sigma.numel(), _lib.stream_ptr()),
                    "tir_composite_bwd")
         return g_sigma, None, None, None
 
@@ -186,9 +186,11 @@ def composite(sigma, dist, offsets, scale):
 
 
 def valid_samples(model, rays_o, rays_d, *, n_samples=-1, jitter=None, table=None, counters=None, no_bbox=False,
-                  count_only=False):
+                  count_only=False, capacity=None):
     """Ray-sorted list of the samples that are inside the aabb and pass the alpha mask.
-    -> dict(ray, sample, xn, z, dist, offsets, counts)."""
+    -> dict(ray, sample, xn, z, dist, offsets, counts).
+    ``capacity``: static list length (no host sync; rows past the real total are zero padding, rows that do not fit
+    are dropped and flagged in ``overflow``) — the shape-static form used under CUDA-graph capture."""
     lib = _lib.load()
     f = ops.device_field(model).refresh(model)
     keep = []
@@ -208,16 +210,25 @@ def valid_samples(model, rays_o, rays_d, *, n_samples=-1, jitter=None, table=Non
         return {"counts": counts}
     offsets = torch.zeros(n + 1, dtype=torch.int64, device=dev)
     torch.cumsum(counts, 0, out=offsets[1:])
-    total = int(offsets[-1].item())
+    if capacity is None:
+        total = int(offsets[-1].item())
+        alloc = torch.empty
+        cap_arg = 0
+    else:
+        total = int(capacity)
+        alloc = torch.zeros
+        cap_arg = total
     out = {"counts": counts, "offsets": offsets,
-           "ray": torch.empty(total, dtype=torch.int32, device=dev),
-           "sample": torch.empty(total, dtype=torch.int32, device=dev),
-           "xn": torch.empty(total, 3, device=dev), "z": torch.empty(total, device=dev),
-           "dist": torch.empty(total, device=dev)}
+           "ray": alloc(total, dtype=torch.int32, device=dev),
+           "sample": alloc(total, dtype=torch.int32, device=dev),
+           "xn": alloc((total, 3), device=dev), "z": alloc(total, device=dev),
+           "dist": alloc(total, device=dev)}
+    if capacity is not None:
+        out["overflow"] = offsets[-1] > total
     if total > 0:
         _lib.check(lib.tir_valid_samples_fill(C.byref(f), _lib.dptr(ro), _lib.dptr(rd), n, C.byref(cfg),
                                               _lib.dptr(offsets, torch.int64), _lib.dptr(out["ray"], torch.int32),
                                               _lib.dptr(out["sample"], torch.int32), _lib.dptr(out["xn"]),
-                                              _lib.dptr(out["z"]), _lib.dptr(out["dist"]), _lib.stream_ptr()),
+                                              _lib.dptr(out["z"]), _lib.dptr(out["dist"]), cap_arg, _lib.stream_ptr()),
                    "tir_valid_samples_fill")
     return out

@@ -278,3 +278,66 @@ def test_full_size_properties():
     # telescoping identity of raw2alpha: sum_i alpha_i T_i = 1 - prod_i (1 - alpha_i)  =>  acc + T_last = 1
     close(acc + t, torch.ones_like(t), 1e-5, "acc + T_last")
     assert float(dep[hit].min()) > 2.0 and float(dep[hit].max()) < 6.0
+
+
+def _train_loss(got):
+    target = torch.full_like(got["rgb_map"], 0.5)
+    return (((got["rgb_map"] - target) ** 2).mean() + 0.2 * ((got["rgb_with_brdf_map"] - target) ** 2).mean()
+            + 0.0005 * got["normals_diff_map"].mean() + 0.001 * got["normals_orientation_loss_map"].mean()
+            + 0.001 * got["albedo_smoothness_loss"] + 0.001 * got["roughness_smoothness_loss"])
+
+
+def test_static_capacity_mode_matches_dynamic(golden_rotated):
+    """The shape-static form used under CUDA-graph capture (padded lists, no acc_mask compaction) gives the same maps
+    and gradients as the dynamic path for identical random inputs."""
+    from tensoir_b200 import Renderer_TensoIR_train
+    fx = golden_rotated
+    rays, li = fx["rays"].to(DEV), fx["light_idx"].to(DEV)
+    noise = lambda t: torch.sin(t * 977.0)          # deterministic per row, independent of padding
+    outs = []
+    for static in (False, True):
+        m = model_from_fixture(fx, DEV)
+        m.__dict__["_tir_randn_like"] = noise
+        torch.manual_seed(5)
+        if static:
+            jit = torch.rand(64, 1)
+            dirs = m.gen_light_incident_dirs(method='stratified_sampling')
+            m.__dict__["_tir_static"] = {"cap_valid": 64 * 60, "cap_app": 1024, "jitter": jit.to(DEV),
+                                         "dirs": dirs.to(DEV), "overflow": torch.zeros((), dtype=torch.int64, device=DEV)}
+        got = Renderer_TensoIR_train(rays, None, li, m, N_samples=60, white_bg=True, is_train=True, is_relight=True,
+                                     sample_method='stratified_sampling', device=DEV, args=renderer_args(24))
+        loss = _train_loss(got)
+        loss.backward()
+        if static:
+            assert int(m.__dict__["_tir_static"]["overflow"]) == 0
+        outs.append((got, loss, {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}))
+    (g0, l0, gr0), (g1, l1, gr1) = outs
+    for k in g0:
+        close(g1[k], g0[k], 2e-5, k)
+    close(l1, l0, 2e-5, "loss")
+    assert set(gr0) == set(gr1)
+    for k in gr0:
+        scale = float(gr0[k].abs().max()) + 1e-12
+        assert float((gr0[k] - gr1[k]).abs().max()) / scale < 1e-3, k
+
+
+def test_cuda_graph_step(golden_rotated):
+    """Whole-step capture: replays run, stay finite, never overflow, move the parameters, and the captured loss of the
+    first replay equals the eager static step on the same inputs (up to the xyz-noise stream, weight 1e-3)."""
+    from tensoir_b200.static_step import StaticTrainStep
+    fx = golden_rotated
+    m = model_from_fixture(fx, DEV)
+    opt = torch.optim.Adam(m.get_optparam_groups(0.02, 0.001), betas=(0.9, 0.99), fused=True, capturable=True)
+    rays, li = fx["rays"].to(DEV), fx["light_idx"].to(DEV)
+    # the loss also touches parameters directly (L1 regulariser, train_tensoIR.py:271-273): a second gradient producer
+    st = StaticTrainStep(m, opt, 64, 60, renderer_args(24), lambda ret, mm: _train_loss(ret) + 4e-5 * mm.density_L1(),
+                         device=DEV)
+    st.calibrate([(rays, li)])
+    before = m.density_plane[0].detach().clone()
+    st.capture(warmup=2)
+    losses = [float(st.run(rays, li)) for _ in range(4)]
+    assert all(l == l and l < 10 for l in losses), losses
+    assert st.overflowed() == 0
+    assert float((m.density_plane[0] - before).abs().max()) > 0
+    assert losses[-1] < losses[0] + 1e-3          # Adam on a fixed batch does not diverge
+    st.release()
