@@ -13,12 +13,15 @@ namespace {
 
 constexpr int kWarpsPerBlock = 8;
 constexpr int kQueue = 64;
-constexpr int kBlocksPerSM = 3;
+constexpr int kBlocksPerSM = 2;
 
 struct QEntry {
   float x, y, z;   // normalised coords
+  float zs;        // z value of the sample
+  float dist;      // z[s+1] - z[s] (0 for the last sample)
   int s;           // sample index along the ray
-};
+  int ray;         // ray the sample belongs to
+};                 // 7 words: odd stride => conflict-free per-lane access
 
 struct MarchParams {
   TirField f;
@@ -41,6 +44,34 @@ struct MarchParams {
   unsigned long long* counters;
 };
 
+// Segmented warp scans over lanes whose segment heads are flagged (consecutive samples of one ray form a segment).
+__device__ __forceinline__ float seg_scan_mul(float v, bool head, int lane) {
+  bool f = head;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float vu = __shfl_up_sync(0xffffffffu, v, o);
+    const bool fu = __shfl_up_sync(0xffffffffu, (int)f, o) != 0;
+    if (lane >= o) {
+      if (!f) v = __fmul_rn(vu, v);
+      f = f | fu;
+    }
+  }
+  return v;
+}
+__device__ __forceinline__ float seg_scan_add(float v, bool head, int lane) {
+  bool f = head;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float vu = __shfl_up_sync(0xffffffffu, v, o);
+    const bool fu = __shfl_up_sync(0xffffffffu, (int)f, o) != 0;
+    if (lane >= o) {
+      if (!f) v += vu;
+      f = f | fu;
+    }
+  }
+  return v;
+}
+
 template <int C, int SAMPLING, bool WITH_APP, bool DENSE>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, kBlocksPerSM) march_kernel(const MarchParams p) {
   __shared__ QEntry queue[kWarpsPerBlock][kQueue];
@@ -50,14 +81,86 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, kBlocksPerSM) march_kerne
   const TirField& f = p.f;
   const int N = p.cfg.n_samples;
   const float scale = f.distance_scale;
+  const bool need_sums = (p.acc != nullptr) | (p.depth != nullptr);
   unsigned long long c_mask = 0, c_density = 0, c_app = 0, c_rays = 0, c_over = 0;
 
+  // Valid samples of CONSECUTIVE rays share 32-lane gather batches (a ray rarely has a multiple of 32 valid samples;
+  // flushing per ray left the 72-load gather ~40 % occupied).  The compositing scan is segmented by ray; the state of
+  // the one ray that may straddle two batches is carried in (c_ray, c_T, c_acc, c_dep).
+  int qn = 0;
+  int c_ray = -1;
+  float c_T = 1.f, c_acc = 0.f, c_dep = 0.f;
+
+  // gather + composite the first `nb` queue entries (nb <= 32).  Segments of rays other than `open_ray` are complete.
+  auto process = [&](int nb, int open_ray) {
+    const bool active = lane < nb;
+    const QEntry e = q[active ? lane : 0];
+    const int ray_l = active ? e.ray : -2 - lane;
+    float sigma = 0.f;
+    if (active) sigma = feature_to_sigma(f, density_feature<C>(f, e.x, e.y, e.z));
+    // raw2alpha: alpha = 1 - exp(-sigma * (dist*scale)); T = cumprod(1 - alpha + 1e-10)
+    const float alpha = active ? __fsub_rn(1.f, expf(__fmul_rn(-sigma, __fmul_rn(e.dist, scale)))) : 0.f;
+    const int prev_ray = __shfl_up_sync(0xffffffffu, ray_l, 1);
+    const int next_ray = __shfl_down_sync(0xffffffffu, ray_l, 1);
+    const bool head = (lane == 0) | (prev_ray != ray_l);
+    const bool tail = active & ((lane == 31) | (next_ray != ray_l));
+    const bool cont = (ray_l == c_ray);                       // continues the carried ray
+    const float incl = seg_scan_mul(__fadd_rn(__fsub_rn(1.f, alpha), 1e-10f), head, lane);
+    const float incl_prev = __shfl_up_sync(0xffffffffu, incl, 1);
+    const float start = cont ? c_T : 1.f;
+    const float excl = __fmul_rn(start, head ? 1.f : incl_prev);
+    const float w = __fmul_rn(alpha, excl);
+    const float seg_T = __fmul_rn(start, incl);
+    float seg_acc = 0.f, seg_dep = 0.f;
+    if (need_sums) {
+      seg_acc = seg_scan_add(w, head, lane) + (cont ? c_acc : 0.f);
+      seg_dep = seg_scan_add(w * e.zs, head, lane) + (cont ? c_dep : 0.f);
+    }
+    if (tail & (ray_l != open_ray)) {                         // ray complete: emit its outputs
+      if (p.t_last) p.t_last[ray_l] = seg_T;
+      if (p.acc) p.acc[ray_l] = seg_acc;
+      if (p.depth) p.depth[ray_l] = seg_dep;
+    }
+    // carry the straddling ray (if the last entry belongs to the ray still being sampled)
+    const int last_ray = __shfl_sync(0xffffffffu, ray_l, nb - 1);
+    const float last_T = __shfl_sync(0xffffffffu, seg_T, nb - 1);
+    const float last_acc = __shfl_sync(0xffffffffu, seg_acc, nb - 1);
+    const float last_dep = __shfl_sync(0xffffffffu, seg_dep, nb - 1);
+    if (last_ray == open_ray) { c_ray = last_ray; c_T = last_T; c_acc = last_acc; c_dep = last_dep; }
+    else { c_ray = -1; c_T = 1.f; c_acc = 0.f; c_dep = 0.f; }
+    if (WITH_APP) {
+      const bool app = active && (w > f.weight_thres);
+      const unsigned m = __ballot_sync(0xffffffffu, app);
+      if (m) {
+        unsigned base = 0;
+        const int cnt = __popc(m);
+        if (lane == 0) base = atomicAdd(p.sample_count, (unsigned)cnt);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (app) {
+          const unsigned slot = base + __popc(m & ((1u << lane) - 1u));
+          if ((int64_t)slot < p.capacity) {
+            TirAppSample sm;
+            sm.xn[0] = e.x; sm.xn[1] = e.y; sm.xn[2] = e.z; sm.weight = w; sm.ray = e.ray; sm.sample = e.s;
+            p.samples[slot] = sm;
+            c_app += 1;
+          } else {
+            c_over += 1;
+          }
+        }
+      }
+    } else {
+      c_app += (active && (w > f.weight_thres));
+    }
+    c_density += active;
+  };
+
   const int64_t warp_stride = (int64_t)gridDim.x * kWarpsPerBlock;
-  for (int64_t ray = (int64_t)blockIdx.x * kWarpsPerBlock + warp; ray < p.n_rays; ray += warp_stride) {
+  for (int64_t ray64 = (int64_t)blockIdx.x * kWarpsPerBlock + warp; ray64 < p.n_rays; ray64 += warp_stride) {
+    const int ray = (int)ray64;
     float ox, oy, oz, dx, dy, dz;
     if (DENSE) {
-      const int64_t pt = ray / p.n_dirs;
-      const int di = (int)(ray - pt * p.n_dirs);
+      const int64_t pt = ray64 / p.n_dirs;
+      const int di = (int)(ray64 - pt * p.n_dirs);
       dx = __ldg(p.dirs + di * 3 + 0); dy = __ldg(p.dirs + di * 3 + 1); dz = __ldg(p.dirs + di * 3 + 2);
       const float nx = __ldg(p.normals + pt * 3 + 0), ny = __ldg(p.normals + pt * 3 + 1),
                   nz = __ldg(p.normals + pt * 3 + 2);
@@ -66,8 +169,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, kBlocksPerSM) march_kerne
       if (!(cosine > 1e-6f)) continue;
       ox = __ldg(p.surf_xyz + pt * 3 + 0); oy = __ldg(p.surf_xyz + pt * 3 + 1); oz = __ldg(p.surf_xyz + pt * 3 + 2);
     } else {
-      ox = __ldg(p.rays_o + ray * 3 + 0); oy = __ldg(p.rays_o + ray * 3 + 1); oz = __ldg(p.rays_o + ray * 3 + 2);
-      dx = __ldg(p.rays_d + ray * 3 + 0); dy = __ldg(p.rays_d + ray * 3 + 1); dz = __ldg(p.rays_d + ray * 3 + 2);
+      ox = __ldg(p.rays_o + ray64 * 3 + 0); oy = __ldg(p.rays_o + ray64 * 3 + 1); oz = __ldg(p.rays_o + ray64 * 3 + 2);
+      dx = __ldg(p.rays_d + ray64 * 3 + 0); dy = __ldg(p.rays_d + ray64 * 3 + 1); dz = __ldg(p.rays_d + ray64 * 3 + 2);
     }
     c_rays += (lane == 0);
 
@@ -80,72 +183,20 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, kBlocksPerSM) march_kerne
       const float az = __fdiv_rn(__fsub_rn(f.aabb_hi[2], oz), vz), bz = __fdiv_rn(__fsub_rn(f.aabb_lo[2], oz), vz);
       tmin = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
       tmin = fminf(fmaxf(tmin, p.cfg.near), p.cfg.far);
-      jit = p.cfg.jitter ? __ldg(p.cfg.jitter + ray) : 0.f;
+      jit = p.cfg.jitter ? __ldg(p.cfg.jitter + ray64) : 0.f;
     }
     auto z_of = [&](int s) -> float {
       if (SAMPLING == TIR_SAMPLE_STEP) return __fadd_rn(tmin, __fmul_rn(p.cfg.step, __fadd_rn((float)s, jit)));
       return __ldg(p.cfg.z_table + s);
     };
 
-    float carry = 1.f, acc = 0.f, dep = 0.f;
-    int qn = 0;
-
-    // gather + composite the first `nb` queue entries (nb <= 32), in ray order
-    auto process = [&](int nb) {
-      float sigma = 0.f, zs = 0.f, dist = 0.f;
-      QEntry e = q[lane < nb ? lane : 0];
-      const bool active = lane < nb;
-      if (active) {
-        sigma = feature_to_sigma(f, density_feature<C>(f, e.x, e.y, e.z));
-        zs = z_of(e.s);
-        dist = (e.s + 1 < N) ? __fsub_rn(z_of(e.s + 1), zs) : 0.f;
-      }
-      // raw2alpha: alpha = 1 - exp(-sigma * (dist*scale)); T = cumprod(1 - alpha + 1e-10)
-      const float alpha = active ? __fsub_rn(1.f, expf(__fmul_rn(-sigma, __fmul_rn(dist, scale)))) : 0.f;
-      float incl = __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        float up = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl = __fmul_rn(incl, up);
-      }
-      float excl = __shfl_up_sync(0xffffffffu, incl, 1);
-      excl = __fmul_rn(carry, lane ? excl : 1.f);
-      const float w = __fmul_rn(alpha, excl);
-      acc += w;
-      dep = fmaf(w, zs, dep);
-      carry = __fmul_rn(carry, __shfl_sync(0xffffffffu, incl, 31));
-      if (WITH_APP) {
-        const bool app = active && (w > f.weight_thres);
-        const unsigned m = __ballot_sync(0xffffffffu, app);
-        if (m) {
-          unsigned base = 0;
-          const int cnt = __popc(m);
-          if (lane == 0) base = atomicAdd(p.sample_count, (unsigned)cnt);
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (app) {
-            const unsigned slot = base + __popc(m & ((1u << lane) - 1u));
-            if ((int64_t)slot < p.capacity) {
-              TirAppSample sm;
-              sm.xn[0] = e.x; sm.xn[1] = e.y; sm.xn[2] = e.z; sm.weight = w; sm.ray = (int)ray; sm.sample = e.s;
-              p.samples[slot] = sm;
-              c_app += 1;
-            } else {
-              c_over += 1;
-            }
-          }
-        }
-      } else {
-        c_app += (active && (w > f.weight_thres));
-      }
-      c_density += active;
-    };
-
+    int pushed = 0;
     for (int base = 0; base < N; base += 32) {
       const int s = base + lane;
       bool valid = false;
-      float nx = 0.f, ny = 0.f, nz = 0.f;
+      float nx = 0.f, ny = 0.f, nz = 0.f, z = 0.f;
       if (s < N) {
-        const float z = z_of(s);
+        z = z_of(s);
         const float px = __fadd_rn(ox, __fmul_rn(dx, z)), py = __fadd_rn(oy, __fmul_rn(dy, z)),
                     pz = __fadd_rn(oz, __fmul_rn(dz, z));
         const bool out = (f.aabb_lo[0] > px) | (px > f.aabb_hi[0]) | (f.aabb_lo[1] > py) | (py > f.aabb_hi[1]) |
@@ -164,13 +215,16 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, kBlocksPerSM) march_kerne
       }
       const unsigned m = __ballot_sync(0xffffffffu, valid);
       if (valid) {
-        QEntry e; e.x = nx; e.y = ny; e.z = nz; e.s = s;
+        QEntry e;
+        e.x = nx; e.y = ny; e.z = nz; e.zs = z; e.s = s; e.ray = ray;
+        e.dist = (s + 1 < N) ? __fsub_rn(z_of(s + 1), z) : 0.f;
         q[qn + __popc(m & ((1u << lane) - 1u))] = e;
       }
       qn += __popc(m);
+      pushed += __popc(m);
       __syncwarp();
       if (qn >= 32) {
-        process(32);
+        process(32, ray);
         __syncwarp();
         const int rest = qn - 32;
         QEntry mv;
@@ -181,17 +235,24 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, kBlocksPerSM) march_kerne
         __syncwarp();
       }
     }
-    if (qn > 0) process(qn);
-    __syncwarp();
-
-    acc = warp_sum(acc);
-    dep = warp_sum(dep);
-    if (lane == 0) {
-      if (p.t_last) p.t_last[ray] = carry;
-      if (p.acc) p.acc[ray] = acc;
-      if (p.depth) p.depth[ray] = dep;
+    // the ray is complete; if none of its samples is still queued its outputs are final now
+    const bool queued = (qn > 0) && (q[qn - 1].ray == ray);
+    if (!queued) {
+      if (c_ray == ray) {
+        if (lane == 0) {
+          if (p.t_last) p.t_last[ray] = c_T;
+          if (p.acc) p.acc[ray] = c_acc;
+          if (p.depth) p.depth[ray] = c_dep;
+        }
+        c_ray = -1; c_T = 1.f; c_acc = 0.f; c_dep = 0.f;
+      } else if (pushed == 0 && lane == 0) {
+        if (p.t_last) p.t_last[ray] = 1.f;
+        if (p.acc) p.acc[ray] = 0.f;
+        if (p.depth) p.depth[ray] = 0.f;
+      }
     }
   }
+  if (qn > 0) process(qn, -1);
 
   c_mask = warp_sum_u64(c_mask); c_density = warp_sum_u64(c_density); c_app = warp_sum_u64(c_app);
   c_rays = warp_sum_u64(c_rays); c_over = warp_sum_u64(c_over);

@@ -90,7 +90,7 @@ def forward_relight(model, rays_chunk, light_idx, white_bg=True, is_train=False,
         n_app = app_idx.shape[0]
         if cnt is not None:
             cnt[2] += n_app
-        w_a = weight[app_idx]
+        w_a = weight.index_select(0, app_idx)
     else:
         # static capacity: padded index list, padding rows carry weight 0 (and therefore no gradient)
         app_idx = torch.nonzero_static(app_sel, size=st["cap_app"], fill_value=-1).reshape(-1)
@@ -101,9 +101,9 @@ def forward_relight(model, rays_chunk, light_idx, white_bg=True, is_train=False,
         st["overflow"] += (n_real > st["cap_app"]).to(st["overflow"].dtype)
         if cnt is not None:
             cnt[2] += n_real
-        w_a = weight[app_idx] * real.to(weight.dtype)
-    r_a = ray_id[app_idx]
-    x_a = xn[app_idx]
+        w_a = weight.index_select(0, app_idx) * real.to(weight.dtype)
+    r_a = ray_id.index_select(0, app_idx)
+    x_a = xn.index_select(0, app_idx)
 
     acc_map = _segment_sum(weight, ray_id, n_rays)
     depth_map = _segment_sum(weight * m["z"], ray_id, n_rays)
@@ -113,12 +113,13 @@ def forward_relight(model, rays_chunk, light_idx, white_bg=True, is_train=False,
     rgb_map, normal_map, albedo_map = z3, z3.clone(), z3.clone()
     roughness_map, nd_map, no_map, ac_map, rc_map = z1, z1.clone(), z1.clone(), z1.clone(), z1.clone()
     if n_app > 0:
-        vd = viewdirs[r_a]
-        li = light_idx.reshape(-1)[r_a]
+        vd = viewdirs.index_select(0, r_a)
+        li = light_idx.reshape(-1).index_select(0, r_a)
         rad, intr = model.compute_bothfeature(x_a, li)
         rgb = model.renderModule(x_a, vd, rad)
-        rgb_map = _segment_sum(w_a[:, None] * rgb, r_a, n_rays)
-        if is_relight:
+        if not is_relight:
+            rgb_map = _segment_sum(w_a[:, None] * rgb, r_a, n_rays)
+        else:
             brdf = model.renderModule_brdf(x_a, intr)
             v_alb, v_rough = brdf[..., :3], (brdf[..., 3:4] * 0.9 + 0.09)
             # device-side draw, same shape/order as torch.randn_like(xyz_sampled[app_mask]) (tensorBase:937)
@@ -127,25 +128,25 @@ def forward_relight(model, rays_chunk, light_idx, white_bg=True, is_train=False,
             brdf_j = model.renderModule_brdf(x_j, model.compute_intrinfeature(x_j))
             a_cost = model.compute_relative_smoothness_loss(v_alb, brdf_j[..., :3])
             r_cost = model.compute_relative_smoothness_loss(v_rough, brdf_j[..., 3:4] * 0.9 + 0.09)
+            zero1 = torch.zeros_like(a_cost)
             if model.normals_kind == "purely_predicted":
                 v_n = model.renderModule_normal(x_a, intr)
-                nd = no = None
+                nd = no = zero1
             elif model.normals_kind == "purely_derived":
                 v_n = _derived_normals(model, x_a)
-                nd = no = None
+                nd = no = zero1
             else:  # derived_plus_predicted
                 d_n = _derived_normals(model, x_a)
                 v_n = model.renderModule_normal(x_a, intr)
                 nd = torch.sum(torch.pow(v_n - d_n, 2), dim=-1, keepdim=True)
                 no = torch.sum(vd * v_n, dim=-1, keepdim=True).clamp(min=0)
-            normal_map = _segment_sum(w_a[:, None] * v_n, r_a, n_rays)
-            albedo_map = _segment_sum(w_a[:, None] * v_alb, r_a, n_rays)
-            roughness_map = _segment_sum(w_a[:, None] * v_rough, r_a, n_rays)
-            ac_map = _segment_sum(w_a[:, None] * a_cost, r_a, n_rays)
-            rc_map = _segment_sum(w_a[:, None] * r_cost, r_a, n_rays)
-            if nd is not None:
-                nd_map = _segment_sum(w_a[:, None] * nd, r_a, n_rays)
-                no_map = _segment_sum(w_a[:, None] * no, r_a, n_rays)
+            # all 14 per-sample channels composited with ONE segment sum: [rgb 3 | normal 3 | albedo 3 | rough 1 |
+            # albedo cost 1 | rough cost 1 | normals_diff 1 | orientation 1]
+            packed = _segment_sum(w_a[:, None] * torch.cat([rgb, v_n, v_alb, v_rough, a_cost, r_cost, nd, no], dim=-1),
+                                  r_a, n_rays)
+            rgb_map, normal_map, albedo_map = packed[:, 0:3], packed[:, 3:6], packed[:, 6:9]
+            roughness_map, ac_map, rc_map = packed[:, 9:10], packed[:, 10:11], packed[:, 11:12]
+            nd_map, no_map = packed[:, 12:13], packed[:, 13:14]
 
     def bg():
         # white_bg short-circuits the CPU coin (tensorBase:979 / :1004)
@@ -191,10 +192,11 @@ def forward_init(model, rays_chunk, white_bg=True, is_train=False, N_samples=-1)
     acc_map = _segment_sum(weight, ray_id, n_rays)
     rgb_map = torch.zeros(n_rays, 3, device=rays.device)
     if app_idx.shape[0] > 0:
-        r_a = ray_id[app_idx]
-        feats = model.compute_appfeature(xn[app_idx])
-        rgb = model.renderModule(xn[app_idx], rays[:, 3:6][r_a], feats)
-        rgb_map = _segment_sum(weight[app_idx][:, None] * rgb, r_a, n_rays)
+        r_a = ray_id.index_select(0, app_idx)
+        x_a = xn.index_select(0, app_idx)
+        feats = model.compute_appfeature(x_a)
+        rgb = model.renderModule(x_a, rays[:, 3:6].index_select(0, r_a), feats)
+        rgb_map = _segment_sum(weight.index_select(0, app_idx)[:, None] * rgb, r_a, n_rays)
     if white_bg or (is_train and bool(torch.rand((1,)) < 0.5)):
         rgb_map = rgb_map + (1. - acc_map[..., None])
     rgb_map = rgb_map.clamp(0, 1)

@@ -270,7 +270,11 @@ def test_full_size_properties():
     assert float(t.min()) >= 0 and float(t.max()) <= 1 + 1e-6 and float(acc.max()) <= 1 + 1e-5
     t1, a1, d1 = ops.march_density(m, rays[:2048, :3], rays[:2048, 3:], n_samples=443)
     t2, a2, d2 = ops.march_density(m, rays[2048:, :3], rays[2048:, 3:], n_samples=443)
-    assert torch.equal(torch.cat([t1, t2]), t) and torch.equal(torch.cat([a1, a2]), acc)
+    # chunking invariance (batches of the gather are shared across consecutive rays, so the scan association - not
+    # the math - depends on the neighbours: equal to fp32 round-off, not bit-for-bit)
+    close(torch.cat([t1, t2]), t, 2e-6, "T chunking")
+    close(torch.cat([a1, a2]), acc, 2e-6, "acc chunking")
+    close(torch.cat([d1, d2]), dep, 2e-6, "depth chunking")
     c = ops.counters_dict(cnt)
     assert c["rays"] == 4096 and 0 < c["density"] <= c["mask"] <= 4096 * 443
     hit = acc > 0.5
