@@ -284,9 +284,18 @@ def main():
     if graphed is not None:
         graphed.release()
 
-    if rank != 0:
+    def finish():
+        """Leave together: a CUDA graph holding NCCL kernels plus communicator teardown can hang at interpreter exit,
+        so every rank meets at one last barrier and exits without running destructors."""
+        sys.stdout.flush()
+        sys.stderr.flush()
         if world > 1:
-            dist.destroy_process_group()
+            torch.cuda.synchronize()
+            dist.barrier()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
 
     # ---- roofline of the dominant kernel (the secondary march), timed live with CUDA events on the launch stream
@@ -307,8 +316,7 @@ def main():
         line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": "port",
                                 "sample": cb["sample"]}
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 def roofline(model, batch, n_s, dev, a):

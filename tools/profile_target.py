@@ -32,4 +32,11 @@ for _ in range(a.reps):
     st.march()
     st.mlp()
 torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(20):
+    st.march()
+e1.record()
+torch.cuda.synchronize()
+print("march_ms", e0.elapsed_time(e1) / 20, "unroll", os.environ.get("TIR_MARCH_UNROLL"), "coarse", os.environ.get("TIR_MARCH_COARSE"))
 print("counters", ops.counters_dict(st.counters), "pts", surf.shape[0])
