@@ -35,7 +35,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=300)
     ap.add_argument("--batch", type=int, default=4096)
-    ap.add_argument("--cpu-rays", type=int, default=1024, help="bounded CPU-baseline sample (primary rays / step)")
+    ap.add_argument("--cpu-rays", type=int, default=64, help="bounded CPU-baseline sample (primary rays / step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="do not capture the step into a CUDA graph")
     return ap.parse_args()
@@ -307,7 +307,9 @@ def main():
             "secondary_rays_per_s": (cnt["rays"] - a.batch * a.steps * world) / (ms * 1e-3),
             "counters_per_step": {k: v / a.steps for k, v in cnt.items()},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
-                    "h2d_bytes_per_step": a.batch * (6 * 4 + 4) * world, "d2h_bytes_per_step": 4 * world},
+                    # rays + light_idx + the host-drawn per-ray jitter and stratified light directions
+                    "h2d_bytes_per_step": (a.batch * (6 * 4 + 4) + a.batch * 4 + 512 * 3 * 4) * world,
+                    "d2h_bytes_per_step": 4 * world},
             "gpu_launches": launches, "clocks": clk, "roofline": roof,
             "execution": ("eager" if a.eager else f"cuda-graph replay of the whole step (static list capacities "
                           f"{caps}, overflowed steps: {overflow})")}

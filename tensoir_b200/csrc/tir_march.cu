@@ -289,6 +289,7 @@ int launch_march(const MarchParams& p, cudaStream_t stream) {
 extern "C" int tir_march_density(const TirField* field, const float* rays_o, const float* rays_d, int64_t n_rays,
                                  const TirMarchCfg* cfg, float* t_last, float* acc, float* depth,
                                  uint64_t* counters, void* stream) {
+  if (n_rays <= 0) return TIR_OK;   // empty input: nothing to do (pointers of empty tensors are NULL)
   if (!field || !cfg || !rays_o || !rays_d) return TIR_ERR_NULL;
   MarchParams p{};
   p.f = *field; p.cfg = *cfg; p.rays_o = rays_o; p.rays_d = rays_d; p.n_rays = n_rays;
@@ -301,6 +302,7 @@ extern "C" int tir_march_radiance(const TirField* field, const TirMlp* mlp, cons
                                   float* t_last, float* acc, float* depth, float* rgb,
                                   TirAppSample* samples, uint32_t* sample_count, int64_t capacity,
                                   uint64_t* counters, void* stream) {
+  if (n_rays <= 0) return TIR_OK;   // empty input: nothing to do (pointers of empty tensors are NULL)
   if (!field || !mlp || !cfg || !rays_o || !rays_d || !rgb || !samples || !sample_count) return TIR_ERR_NULL;
   if (capacity <= 0) return TIR_ERR_CAPACITY;
   MarchParams p{};
@@ -316,6 +318,7 @@ extern "C" int tir_secondary_march(const TirField* field, const float* surf_xyz,
                                   int64_t n_pts, const float* dirs, int32_t n_dirs, const TirMarchCfg* cfg,
                                   float* vis, TirAppSample* samples, uint32_t* sample_count, int64_t capacity,
                                   uint64_t* counters, void* stream) {
+  if (n_pts <= 0) return TIR_OK;   // empty input: nothing to do (pointers of empty tensors are NULL)
   if (!field || !cfg || !surf_xyz || !normals || !dirs || !vis || !samples || !sample_count) return TIR_ERR_NULL;
   if (n_dirs <= 0) return TIR_ERR_SHAPE;
   if (capacity <= 0) return TIR_ERR_CAPACITY;
@@ -332,6 +335,7 @@ extern "C" int tir_secondary_radiance(const TirField* field, const TirMlp* mlp, 
                                       const float* dirs, int32_t n_dirs, const TirMarchCfg* cfg, float* vis,
                                       float* indirect, TirAppSample* samples, uint32_t* sample_count,
                                       int64_t capacity, uint64_t* counters, void* stream) {
+  if (n_pts <= 0) return TIR_OK;   // empty input: nothing to do (pointers of empty tensors are NULL)
   if (!mlp || !indirect) return TIR_ERR_NULL;
   int rc = tir_secondary_march(field, surf_xyz, normals, n_pts, dirs, n_dirs, cfg, vis, samples, sample_count,
                                capacity, counters, stream);

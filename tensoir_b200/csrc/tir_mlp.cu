@@ -370,6 +370,7 @@ extern "C" int tir_app_mlp(const TirField* field, const TirMlp* mlp, const TirAp
 
 extern "C" int tir_app_mlp_points(const TirField* field, const TirMlp* mlp, const float* xn, const float* x_in,
                                   const int32_t* light_idx, int64_t n, int32_t act, float* out, void* stream) {
+  if (n <= 0) return TIR_OK;   // empty input: nothing to do (pointers of empty tensors are NULL)
   if (!field || !mlp || !xn || !x_in || !out) return TIR_ERR_NULL;
   int rc = check_shapes(field, mlp);
   if (rc) return rc;

@@ -95,6 +95,7 @@ __global__ void density_points_kernel(TirField f, const float* __restrict__ xn, 
 
 extern "C" int tir_density_points(const TirField* field, const float* xn, int64_t n, float* feature, float* sigma,
                                   void* stream) {
+  if (n <= 0) return TIR_OK;   // empty input: nothing to do (pointers of empty tensors are NULL)
   if (!field || !xn) return TIR_ERR_NULL;
   if (n <= 0) return TIR_OK;
   int blocks = (int)((n + 127) / 128 < 148 * 16 ? (n + 127) / 128 : 148 * 16);
@@ -113,6 +114,7 @@ __global__ void alpha_points_kernel(TirField f, const float* __restrict__ xyz, i
 }
 
 extern "C" int tir_alpha_mask_points(const TirField* field, const float* xyz, int64_t n, uint8_t* mask, void* stream) {
+  if (n <= 0) return TIR_OK;   // empty input: nothing to do (pointers of empty tensors are NULL)
   if (!field || !xyz || !mask || !field->amask || !field->acell) return TIR_ERR_NULL;
   if (n <= 0) return TIR_OK;
   int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);

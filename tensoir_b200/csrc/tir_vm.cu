@@ -374,6 +374,7 @@ inline int blocks_for(int64_t n, int threads, int cap = 148 * 16) {
 }  // namespace
 
 extern "C" int tir_vm_app_products(const TirField* field, const float* xn, int64_t n, float* out, void* stream) {
+  if (n <= 0) return TIR_OK;   // empty input: nothing to do (pointers of empty tensors are NULL)
   if (!field || !xn || !out) return TIR_ERR_NULL;
   if (field->aC != 48) return TIR_ERR_SHAPE;
   if (n <= 0) return TIR_OK;
@@ -383,6 +384,7 @@ extern "C" int tir_vm_app_products(const TirField* field, const float* xn, int64
 
 extern "C" int tir_vm_app_products_bwd(const TirField* field, const float* xn, int64_t n, const float* g_out,
                                        float* const* g_plane, float* const* g_line, void* stream) {
+  if (n <= 0) return TIR_OK;   // empty input: nothing to do (pointers of empty tensors are NULL)
   if (!field || !xn || !g_out || !g_plane || !g_line) return TIR_ERR_NULL;
   if (field->aC != 48) return TIR_ERR_SHAPE;
   if (n <= 0) return TIR_OK;
@@ -394,6 +396,7 @@ extern "C" int tir_vm_app_products_bwd(const TirField* field, const float* xn, i
 
 extern "C" int tir_vm_density_bwd(const TirField* field, const float* xn, int64_t n, const float* g_feature,
                                   float* const* g_plane, float* const* g_line, void* stream) {
+  if (n <= 0) return TIR_OK;   // empty input: nothing to do (pointers of empty tensors are NULL)
   if (!field || !xn || !g_feature || !g_plane || !g_line) return TIR_ERR_NULL;
   if (field->dC != 16) return TIR_ERR_SHAPE;
   if (n <= 0) return TIR_OK;
@@ -405,6 +408,7 @@ extern "C" int tir_vm_density_bwd(const TirField* field, const float* xn, int64_
 
 extern "C" int tir_vm_density_grad(const TirField* field, const float* xn, int64_t n, float* feature, float* dfdx,
                                    void* stream) {
+  if (n <= 0) return TIR_OK;   // empty input: nothing to do (pointers of empty tensors are NULL)
   if (!field || !xn || !feature || !dfdx) return TIR_ERR_NULL;
   if (field->dC != 16) return TIR_ERR_SHAPE;
   if (n <= 0) return TIR_OK;
@@ -415,6 +419,7 @@ extern "C" int tir_vm_density_grad(const TirField* field, const float* xn, int64
 extern "C" int tir_vm_density_grad_bwd(const TirField* field, const float* xn, int64_t n, const float* g_feature,
                                        const float* g_dfdx, float* const* g_plane, float* const* g_line,
                                        void* stream) {
+  if (n <= 0) return TIR_OK;   // empty input: nothing to do (pointers of empty tensors are NULL)
   if (!field || !xn || !g_plane || !g_line) return TIR_ERR_NULL;
   if (field->dC != 16) return TIR_ERR_SHAPE;
   if (n <= 0) return TIR_OK;
@@ -428,6 +433,7 @@ extern "C" int tir_vm_density_grad_bwd(const TirField* field, const float* xn, i
 extern "C" int tir_valid_samples_count(const TirField* field, const float* rays_o, const float* rays_d,
                                        int64_t n_rays, const TirMarchCfg* cfg, int32_t* counts, uint64_t* counters,
                                        void* stream) {
+  if (n_rays <= 0) return TIR_OK;   // empty input: nothing to do (pointers of empty tensors are NULL)
   if (!field || !rays_o || !rays_d || !cfg || !counts) return TIR_ERR_NULL;
   if (n_rays <= 0) return TIR_OK;
   if (cfg->sampling == TIR_SAMPLE_TABLE && !cfg->z_table) return TIR_ERR_NULL;
@@ -443,6 +449,7 @@ extern "C" int tir_valid_samples_fill(const TirField* field, const float* rays_o
                                       int64_t n_rays, const TirMarchCfg* cfg, const int64_t* offsets,
                                       int32_t* out_ray, int32_t* out_sample, float* out_xn, float* out_z,
                                       float* out_dist, int64_t capacity, void* stream) {
+  if (n_rays <= 0) return TIR_OK;   // empty input: nothing to do (pointers of empty tensors are NULL)
   if (!field || !rays_o || !rays_d || !cfg || !offsets || !out_ray || !out_sample || !out_xn || !out_z || !out_dist)
     return TIR_ERR_NULL;
   if (n_rays <= 0) return TIR_OK;
@@ -457,6 +464,7 @@ extern "C" int tir_valid_samples_fill(const TirField* field, const float* rays_o
 extern "C" int tir_composite_fwd(const float* sigma, const float* dist, const int64_t* offsets, int64_t n_rays,
                                  float distance_scale, float* weight, float* trans, float* t_last, int64_t limit,
                                  void* stream) {
+  if (n_rays <= 0) return TIR_OK;   // empty input: nothing to do (pointers of empty tensors are NULL)
   if (!sigma || !dist || !offsets || !weight || !trans) return TIR_ERR_NULL;
   if (n_rays <= 0) return TIR_OK;
   composite_fwd_kernel<<<(unsigned)((n_rays + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
@@ -467,6 +475,7 @@ extern "C" int tir_composite_fwd(const float* sigma, const float* dist, const in
 extern "C" int tir_composite_bwd(const float* sigma, const float* dist, const int64_t* offsets, int64_t n_rays,
                                  float distance_scale, const float* weight, const float* trans,
                                  const float* g_weight, float* g_sigma, int64_t limit, void* stream) {
+  if (n_rays <= 0) return TIR_OK;   // empty input: nothing to do (pointers of empty tensors are NULL)
   if (!sigma || !dist || !offsets || !weight || !trans || !g_weight || !g_sigma) return TIR_ERR_NULL;
   if (n_rays <= 0) return TIR_OK;
   composite_bwd_kernel<<<(unsigned)((n_rays + 127) / 128), 128, 0, (cudaStream_t)stream>>>(

@@ -345,3 +345,56 @@ def test_cuda_graph_step(golden_rotated):
     assert float((m.density_plane[0] - before).abs().max()) > 0
     assert losses[-1] < losses[0] + 1e-3          # Adam on a fixed batch does not diverge
     st.release()
+
+
+def test_edge_cases(golden_rotated):
+    """Empty and degenerate inputs the reference handles: no rays, rays that miss the aabb entirely (no valid sample,
+    no surface hit -> empty secondary batch), zero direction components (sample_ray's 1e-6 substitution,
+    tensorBase:709), no alpha mask, a single sample per ray."""
+    from tensoir_b200 import Renderer_TensoIR_train, relight_utils as RU, ops
+    fx = golden_rotated
+    m = model_from_fixture(fx, DEV)
+    f = oracle_field(fx)
+    args = renderer_args(24)
+    # (i) zero rays
+    with torch.no_grad():
+        out = Renderer_TensoIR_train(torch.zeros(0, 6), None, torch.zeros(0, 1, dtype=torch.int32), m, N_samples=-1,
+                                     is_train=False, is_relight=True, device=DEV, args=args)
+    assert out["rgb_map"].shape == (0, 3) and out["rgb_with_brdf_map"].shape == (0, 3)
+    nv, nf = RU.compute_transmittance(m, torch.zeros(0, 3, device=DEV), torch.zeros(0, 3, device=DEV), 96, 0.05, 1.5)
+    assert nv.numel() == 0 and nf.numel() == 0
+    # (ii) rays pointing away from the scene + axis-aligned rays with exact zeros in the direction
+    o = torch.tensor([[0., 0., 4.], [0., 0., 4.], [4., 0.2, 0.1], [0.3, -4., 0.2]])
+    d = torch.tensor([[0., 0., 1.], [0., 0., -1.], [-1., 0., 0.], [0., 1., 0.]])
+    rays = torch.cat([o, d], 1)
+    li = torch.zeros(4, 1, dtype=torch.int32)
+    torch.manual_seed(9)
+    m.__dict__["_tir_randn_like"] = lambda t: torch.randn(t.shape).to(t.device)
+    with torch.no_grad():
+        got = Renderer_TensoIR_train(rays, None, li, m, N_samples=-1, is_train=False, is_relight=True, device=DEV,
+                                     args=args)
+    torch.manual_seed(9)
+    want = O.renderer_train(f, rays, li, -1, True, False, True, 'fixed_envirmap', 160000, 24)
+    for k, w in want.items():
+        close(got[k], w, TOL, k)
+    assert float(got["acc_map"][0]) == 0.0            # the ray that leaves the scene composites nothing
+    # (iii) no alpha mask, one sample per ray
+    m2 = model_from_fixture(fx, DEV, with_mask=False)
+    f2 = oracle_field(fx, with_mask=False)
+    r = fx["rays"][:16]
+    t, a, dep = ops.march_density(m2, r[:, :3].to(DEV), r[:, 3:].to(DEV), n_samples=1)
+    pts, z, valid = O.sample_ray(f2, r[:, :3], r[:, 3:6], False, 1)
+    assert torch.equal(a.cpu(), torch.zeros(16))       # a single sample has dist 0 -> alpha 0 (tensorBase:887)
+    t, a, dep = ops.march_density(m2, r[:, :3].to(DEV), r[:, 3:].to(DEV), n_samples=50)
+    _, w, tl = O.raw2alpha(*_oracle_sigma_dist(f2, r, 50))
+    close(a, w.sum(-1), 2e-5, "acc no-mask")
+    close(t, tl.squeeze(-1), 2e-5, "T no-mask")
+
+
+def _oracle_sigma_dist(f, rays, n):
+    pts, z, valid = O.sample_ray(f, rays[:, :3], rays[:, 3:6], False, n)
+    dists = torch.cat((z[:, 1:] - z[:, :-1], torch.zeros_like(z[:, :1])), dim=-1).expand(pts.shape[:-1])
+    sigma = torch.zeros(pts.shape[:-1])
+    xn = O.normalize_coord(f, pts)
+    sigma[valid] = O.feature2density(f, O.density_feature(f, xn[valid]))
+    return sigma, dists * f.distance_scale
