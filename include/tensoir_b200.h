@@ -189,6 +189,13 @@ int tir_app_mlp(const TirField* field, const TirMlp* mlp, const TirAppSample* sa
 int tir_app_mlp_points(const TirField* field, const TirMlp* mlp, const float* xn, const float* x_in,
                        const int32_t* light_idx, int64_t n, int32_t act, float* out, void* stream);
 
+/* tir_app_mlp_points that also dumps the activations a host-side backward needs (training forward of the primary
+ * MLP heads): save_xl [n, 3*aC] light-scaled products, save_in [n, in_dim] MLP input incl. positional encoding,
+ * save_h1 / save_h2 [n, hidden] post-ReLU hidden layers; any of them may be NULL. */
+int tir_app_mlp_points_save(const TirField* field, const TirMlp* mlp, const float* xn, const float* x_in,
+                            const int32_t* light_idx, int64_t n, int32_t act, float* out, float* save_xl,
+                            float* save_in, float* save_h1, float* save_h2, void* stream);
+
 /* ---- modular, autograd-facing half of the primary march (training needs gradients) --------------------- */
 
 /* plane*line products of the appearance tensors on normalised points: xn [n,3] -> out [n, 3*aC]

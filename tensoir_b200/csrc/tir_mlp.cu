@@ -61,6 +61,12 @@ struct MlpParams {
   int64_t n_points;
   float* out;
   int act;        // 0 sigmoid, 1 tanh
+  // optional activation dumps for a host-side backward (training): [n,144] light-scaled products, [n,150] MLP input,
+  // [n,128] hidden 1 / 2 (post-ReLU)
+  float* save_xl;
+  float* save_in;
+  float* save_h1;
+  float* save_h2;
 };
 
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& h, __nv_bfloat16& l) {
@@ -141,6 +147,16 @@ __device__ __forceinline__ void warp_gemm(float (&acc)[MT][NTL][4], const __nv_b
         mma_bf16(acc[mt][nt], fh, bh[nt][0], bh[nt][1]);
       }
     }
+  }
+}
+
+// Write columns [0, ncol) of the activation tile (hi + lo) to a row-major fp32 global array.
+__device__ __forceinline__ void dump_tile(const __nv_bfloat16* ah, const __nv_bfloat16* al, float* dst, int ncol,
+                                          int64_t base, int64_t total, int tid) {
+  for (int i = tid; i < M * ncol; i += NT) {
+    const int row = i / ncol, col = i - row * ncol;
+    if (base + row < total)
+      dst[(base + row) * ncol + col] = __bfloat162float(ah[row * SA + col]) + __bfloat162float(al[row * SA + col]);
   }
 }
 
@@ -236,6 +252,7 @@ __global__ void __launch_bounds__(NT, 1) app_mlp_kernel(const MlpParams p) {
       }
     }
     __syncthreads();
+    if (POINTS && p.save_xl) dump_tile(s.ah, s.al, p.save_xl, K0, base, total, tid);
 
     // ---- phase 2: basis_mat (144 -> 27, N padded to 32): warp w -> m-tile w/2, n-tiles 2*(w%2), +1
     {
@@ -286,6 +303,7 @@ __global__ void __launch_bounds__(NT, 1) app_mlp_kernel(const MlpParams p) {
       }
     }
     __syncthreads();
+    if (POINTS && p.save_in) dump_tile(s.ah, s.al, p.save_in, IN, base, total, tid);
 
     // ---- phases 3/4: hidden layers.  warp w -> all 64 rows x units [16w, 16w+16)
     auto hidden_layer = [&](const __nv_bfloat16* wh, const __nv_bfloat16* wl, int sw, const float* bias, int K) {
@@ -305,7 +323,9 @@ __global__ void __launch_bounds__(NT, 1) app_mlp_kernel(const MlpParams p) {
       __syncthreads();
     };
     hidden_layer(s.w0h, s.w0l, SW0, s.b0, K1);
+    if (POINTS && p.save_h1) dump_tile(s.ah, s.al, p.save_h1, HID, base, total, tid);
     hidden_layer(s.w1h, s.w1l, SW1, s.b1, HID);
+    if (POINTS && p.save_h2) dump_tile(s.ah, s.al, p.save_h2, HID, base, total, tid);
 
     // ---- phase 5: output layer (N padded to 8) on warps 0..3, activation, composite
     if (warp < 4) {
@@ -366,6 +386,21 @@ extern "C" int tir_app_mlp(const TirField* field, const TirMlp* mlp, const TirAp
   p.f = *field; p.mlp = *mlp; p.samples = samples; p.sample_count = sample_count; p.max_samples = max_samples;
   p.ray_dirs = ray_dirs; p.n_dirs = n_dirs; p.light_idx = light_idx; p.rgb_out = rgb_out; p.act = 0;
   return launch<false>(p, max_samples, (cudaStream_t)stream);
+}
+
+extern "C" int tir_app_mlp_points_save(const TirField* field, const TirMlp* mlp, const float* xn, const float* x_in,
+                                       const int32_t* light_idx, int64_t n, int32_t act, float* out, float* save_xl,
+                                       float* save_in, float* save_h1, float* save_h2, void* stream) {
+  if (n <= 0) return TIR_OK;
+  if (!field || !mlp || !xn || !x_in || !out) return TIR_ERR_NULL;
+  int rc = check_shapes(field, mlp);
+  if (rc) return rc;
+  if (act != 0 && act != 1) return TIR_ERR_CONFIG;
+  MlpParams p{};
+  p.f = *field; p.mlp = *mlp; p.pts_xn = xn; p.pts_x = x_in; p.n_points = n; p.light_idx = light_idx;
+  p.out = out; p.act = act;
+  p.save_xl = save_xl; p.save_in = save_in; p.save_h1 = save_h1; p.save_h2 = save_h2;
+  return launch<true>(p, n, (cudaStream_t)stream);
 }
 
 extern "C" int tir_app_mlp_points(const TirField* field, const TirMlp* mlp, const float* xn, const float* x_in,

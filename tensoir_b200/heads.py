@@ -1,0 +1,131 @@
+"""Fused appearance heads for the primary march: appearance gather -> light factor -> basis_mat -> positional
+encoding -> 3-layer MLP in ONE tensor-core kernel launch (csrc/tir_mlp.cu), as a differentiable op.
+
+The forward dumps the activations (light-scaled products, MLP input, both hidden layers); the backward is a short
+hand-written chain of GEMMs on those dumps (no autograd graph, no recomputation) that ends in the appearance scatter
+kernel.  Replaces, per head, compute_{app,intrin}feature + MLPRender_Fea / MLPBRDF_PEandFeature
+(tensoRF_rotated_lights.py:167-224, tensorBase_rotated_lights.py:122-208) and their ~60 autograd nodes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib, ops
+from .device_field import mlp_struct
+from .vm_autograd import _grad_shadows, _ptr_array, _to_param_layout
+
+
+def _wgrad(g, a, splits=32):
+    """g^T @ a for tall-skinny operands ([n, <=128]^T @ [n, <=150], n ~ 2e4).  cuBLAS tiles only the tiny output
+    (6 CTAs on 148 SMs); splitting the reduction over n into `splits` batched GEMMs fills the machine."""
+    n = g.shape[0]
+    per = n // splits
+    if per < 64:
+        return g.t() @ a
+    main = per * splits
+    out = torch.bmm(g[:main].view(splits, per, -1).transpose(1, 2), a[:main].view(splits, per, -1)).sum(0)
+    if main < n:
+        out = out + g[main:].t() @ a[main:]
+    return out
+
+
+class _FusedHead(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, head, light, xn, x_in, li, w0, b0, w1, b1, w2, b2, basis, light_w, *app_params):
+        lib = _lib.load()
+        f = ops.device_field(model).refresh(model)
+        keep = []
+        mlp = mlp_struct(model, head, keep, light=light)
+        n = xn.shape[0]
+        dev = xn.device
+        act = 1 if head == "renderModule_normal" else 0
+        out = torch.empty(n, mlp.out_dim, device=dev)
+        need = any(ctx.needs_input_grad)     # grad mode is off inside Function.forward; this is the real signal
+        k0, in_dim, hid = 3 * f.aC, w0.shape[1], w0.shape[0]
+        xl = torch.empty(n, k0, device=dev) if need else None
+        inp = torch.empty(n, in_dim, device=dev) if need else None
+        h1 = torch.empty(n, hid, device=dev) if need else None
+        h2 = torch.empty(n, hid, device=dev) if need else None
+        nul = C.c_void_p(0)
+        _lib.check(lib.tir_app_mlp_points_save(
+            C.byref(f), C.byref(mlp), _lib.dptr(xn), _lib.dptr(x_in),
+            None if (li is None or light != "index") else _lib.dptr(li, torch.int32), n, act, _lib.dptr(out),
+            _lib.dptr(xl) if need else nul, _lib.dptr(inp) if need else nul, _lib.dptr(h1) if need else nul,
+            _lib.dptr(h2) if need else nul, _lib.stream_ptr()), "tir_app_mlp_points_save")
+        ctx.model, ctx.head, ctx.light, ctx.act = model, head, light, act
+        ctx.n_app_params = len(app_params)
+        ctx.save_for_backward(xn, li if li is not None else torch.empty(0, device=dev), out, xl, inp, h1, h2,
+                              w0, w1, w2, basis, light_w if light_w is not None else torch.empty(0, device=dev))
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        xn, li, out, xl, inp, h1, h2, w0, w1, w2, basis, light_w = ctx.saved_tensors
+        model = ctx.model
+        n = xn.shape[0]
+        g_out = g_out.contiguous()
+        gz3 = g_out * (out * (1 - out) if ctx.act == 0 else 1 - out * out)
+        gw2, gb2 = _wgrad(gz3, h2), gz3.sum(0)
+        gz2 = (gz3 @ w2) * (h2 > 0)
+        gw1, gb1 = _wgrad(gz2, h1), gz2.sum(0)
+        gz1 = (gz2 @ w1) * (h1 > 0)
+        gw0, gb0 = _wgrad(gz1, inp), gz1.sum(0)
+        gin = gz1 @ w0                                           # [n, in_dim]
+        F = basis.shape[0]
+        pe = (inp.shape[1] - F - 3 - 12) // (4 * F) * 2 if False else 2   # fea_pe = 2 (checked by the kernel)
+        s0, c0 = F + 3, F + 3 + F * pe
+        freqs = 2.0 ** torch.arange(pe, device=xn.device, dtype=inp.dtype)
+        gs, gc = gin[:, s0:s0 + F * pe].reshape(n, F, pe), gin[:, c0:c0 + F * pe].reshape(n, F, pe)
+        sn, cs = inp[:, s0:s0 + F * pe].reshape(n, F, pe), inp[:, c0:c0 + F * pe].reshape(n, F, pe)
+        gfeat = gin[:, :F] + ((gs * cs - gc * sn) * freqs).sum(-1)
+        gbasis = _wgrad(gfeat, xl)
+        gxl = gfeat @ basis                                       # [n, 3*aC]
+        # light factor: xl = x0 * lightvec
+        glight = None
+        if ctx.light == "none":
+            gx0 = gxl
+        else:
+            x0 = _raw_products(model, xn)
+            if ctx.light == "index":
+                rows = light_w.index_select(0, li.long())
+                glight = torch.zeros_like(light_w).index_add_(0, li.long(), gxl * x0)
+            else:  # mean over lights
+                rows = light_w.mean(0, keepdim=True)
+                glight = ((gxl * x0).sum(0, keepdim=True) / light_w.shape[0]).expand_as(light_w)
+            gx0 = gxl * rows
+        lib = _lib.load()
+        df = ops.device_field(model)
+        f = df.refresh(model)
+        gp, gl = _grad_shadows(df, "app")
+        gx0 = gx0.contiguous()
+        _lib.check(lib.tir_vm_app_products_bwd(C.byref(f), _lib.dptr(xn), n, _lib.dptr(gx0), _ptr_array(gp),
+                                               _ptr_array(gl), _lib.stream_ptr()), "tir_vm_app_products_bwd")
+        return (None, None, None, None, None, None, gw0, gb0, gw1, gb1, gw2, gb2, gbasis, glight,
+                *_to_param_layout(gp, gl))
+
+
+def _raw_products(model, xn):
+    lib = _lib.load()
+    f = ops.device_field(model).refresh(model)
+    out = torch.empty(xn.shape[0], 3 * f.aC, device=xn.device)
+    _lib.check(lib.tir_vm_app_products(C.byref(f), _lib.dptr(xn), xn.shape[0], _lib.dptr(out), _lib.stream_ptr()),
+               "tir_vm_app_products")
+    return out
+
+
+def fused_head(model, head: str, xn, x_in, light_idx=None, light: str = "index"):
+    """out = act(MLP_head([feat, x_in, PE(feat), PE(x_in)])), feat = basis_mat(plane*line(xn) * lightvec).
+    head: 'renderModule' (x_in = view dir, sigmoid) | 'renderModule_brdf' (x_in = position, sigmoid, 4 outputs) |
+    'renderModule_normal' (position, tanh).  light: 'index' | 'mean' | 'none'."""
+    mod = getattr(model, head)
+    xn = xn.detach().reshape(-1, 3).float().contiguous()
+    x_in = x_in.detach().reshape(-1, 3).float().contiguous()
+    li = None if light_idx is None else light_idx.detach().reshape(-1).to(torch.int32).contiguous()
+    ll = getattr(model, "light_line", None)
+    light_w = None if (ll is None or light == "none") else ll.weight
+    params = list(model.app_plane) + list(model.app_line)
+    return _FusedHead.apply(model, head, light, xn, x_in, li, mod.mlp[0].weight, mod.mlp[0].bias, mod.mlp[2].weight,
+                            mod.mlp[2].bias, mod.mlp[4].weight, mod.mlp[4].bias, model.basis_mat.weight, light_w,
+                            *params)

@@ -11,8 +11,10 @@ from __future__ import annotations
 
 import torch
 import torch.nn.functional as F
+from torch.profiler import record_function
 
 from . import vm_autograd as vm
+from .heads import fused_head
 
 
 def _linear2srgb(t):
@@ -79,9 +81,15 @@ def forward_relight(model, rays_chunk, light_idx, white_bg=True, is_train=False,
     rays = rays_chunk.float()
     n_rays = rays.shape[0]
     viewdirs = rays[:, 3:6]
-    m = march(model, rays, is_train, N_samples, counters=model.__dict__.get("_tir_counters"))
+    with record_function("tir::primary_march"):
+        m = march(model, rays, is_train, N_samples, counters=model.__dict__.get("_tir_counters"))
     ray_id, weight, xn = m["ray_id"], m["weight"], m["xn"]
+    return _forward_relight_tail(model, rays, light_idx, white_bg, is_train, is_relight, m, ray_id, weight, xn, dev,
+                                 n_rays, viewdirs)
 
+
+def _forward_relight_tail(model, rays, light_idx, white_bg, is_train, is_relight, m, ray_id, weight, xn, dev, n_rays,
+                          viewdirs):
     st = model.__dict__.get("_tir_static")
     cnt = model.__dict__.get("_tir_counters")
     app_sel = weight > model.rayMarch_weight_thres
@@ -113,31 +121,32 @@ def forward_relight(model, rays_chunk, light_idx, white_bg=True, is_train=False,
     rgb_map, normal_map, albedo_map = z3, z3.clone(), z3.clone()
     roughness_map, nd_map, no_map, ac_map, rc_map = z1, z1.clone(), z1.clone(), z1.clone(), z1.clone()
     if n_app > 0:
+      with record_function("tir::primary_app_stage"):
         vd = viewdirs.index_select(0, r_a)
         li = light_idx.reshape(-1).index_select(0, r_a)
-        rad, intr = model.compute_bothfeature(x_a, li)
-        rgb = model.renderModule(x_a, vd, rad)
+        # each head = ONE fused kernel launch (gather -> light factor -> basis -> PE -> MLP), see heads.py
+        rgb = fused_head(model, "renderModule", x_a, vd, li, light="index")
         if not is_relight:
             rgb_map = _segment_sum(w_a[:, None] * rgb, r_a, n_rays)
         else:
-            brdf = model.renderModule_brdf(x_a, intr)
+            brdf = fused_head(model, "renderModule_brdf", x_a, x_a, light="mean")
             v_alb, v_rough = brdf[..., :3], (brdf[..., 3:4] * 0.9 + 0.09)
             # device-side draw, same shape/order as torch.randn_like(xyz_sampled[app_mask]) (tensorBase:937)
             draw = model.__dict__.get("_tir_randn_like")       # test hook: replay the oracle's CPU stream
             x_j = x_a + (draw(x_a) if draw is not None else torch.randn_like(x_a)) * 0.01
-            brdf_j = model.renderModule_brdf(x_j, model.compute_intrinfeature(x_j))
+            brdf_j = fused_head(model, "renderModule_brdf", x_j, x_j, light="mean")
             a_cost = model.compute_relative_smoothness_loss(v_alb, brdf_j[..., :3])
             r_cost = model.compute_relative_smoothness_loss(v_rough, brdf_j[..., 3:4] * 0.9 + 0.09)
             zero1 = torch.zeros_like(a_cost)
             if model.normals_kind == "purely_predicted":
-                v_n = model.renderModule_normal(x_a, intr)
+                v_n = fused_head(model, "renderModule_normal", x_a, x_a, light="mean")
                 nd = no = zero1
             elif model.normals_kind == "purely_derived":
                 v_n = _derived_normals(model, x_a)
                 nd = no = zero1
             else:  # derived_plus_predicted
                 d_n = _derived_normals(model, x_a)
-                v_n = model.renderModule_normal(x_a, intr)
+                v_n = fused_head(model, "renderModule_normal", x_a, x_a, light="mean")
                 nd = torch.sum(torch.pow(v_n - d_n, 2), dim=-1, keepdim=True)
                 no = torch.sum(vd * v_n, dim=-1, keepdim=True).clamp(min=0)
             # all 14 per-sample channels composited with ONE segment sum: [rgb 3 | normal 3 | albedo 3 | rough 1 |
@@ -194,8 +203,7 @@ def forward_init(model, rays_chunk, white_bg=True, is_train=False, N_samples=-1)
     if app_idx.shape[0] > 0:
         r_a = ray_id.index_select(0, app_idx)
         x_a = xn.index_select(0, app_idx)
-        feats = model.compute_appfeature(x_a)
-        rgb = model.renderModule(x_a, rays[:, 3:6].index_select(0, r_a), feats)
+        rgb = fused_head(model, "renderModule", x_a, rays[:, 3:6].index_select(0, r_a), None, light="none")
         rgb_map = _segment_sum(weight.index_select(0, app_idx)[:, None] * rgb, r_a, n_rays)
     if white_bg or (is_train and bool(torch.rand((1,)) < 0.5)):
         rgb_map = rgb_map + (1. - acc_map[..., None])

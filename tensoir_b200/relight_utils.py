@@ -12,6 +12,8 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
+from torch.profiler import record_function
+
 from . import ops
 
 
@@ -105,10 +107,19 @@ def render_with_BRDF(depth_map, normal_map, albedo_map, roughness_map, fresnel_m
     surf2l = incident_light_dirs.reshape(1, -1, 3).expand(bs, -1, -1)
     cosine = torch.clamp(torch.einsum("jk,ik->ij", incident_light_dirs, normal_map), min=0.0)
     # secondary rays: cosine test + 96-sample march + appearance MLP, generated on chip per (point, direction)
-    vis, indirect, _ = ops.secondary_radiance(
-        tensoIR, surface_xyz, normal_map, light_idx, incident_light_dirs,
-        n_sample=args.second_nSample, near=args.second_near, far=args.second_far,
-        counters=tensoIR.__dict__.get("_tir_counters"))
+    with record_function("tir::secondary"):
+        vis, indirect, _ = ops.secondary_radiance(
+            tensoIR, surface_xyz, normal_map, light_idx, incident_light_dirs,
+            n_sample=args.second_nSample, near=args.second_near, far=args.second_far,
+            counters=tensoIR.__dict__.get("_tir_counters"))
+    with record_function("tir::shade_epilogue"):
+        return _shade(tensoIR, normal_map, albedo_map, roughness_map, fresnel_map, surf2c, surf2l, cosine, vis, indirect,
+                      incident_light_dirs, light_idx, light_area_weight, nlights, sample_method, use_linear2srgb, device)
+
+
+def _shade(tensoIR, normal_map, albedo_map, roughness_map, fresnel_map, surf2c, surf2l, cosine, vis, indirect,
+           incident_light_dirs, light_idx, light_area_weight, nlights, sample_method, use_linear2srgb, device):
+    """Quadrature of the rendering equation, relight_utils.py:452-483."""
     specular = GGX_specular(normal_map, surf2c, surf2l, roughness_map, fresnel_map)
     surface_brdf = albedo_map.unsqueeze(1).expand(-1, nlights, -1) / np.pi + specular
     envir_map_light_rgbs = tensoIR.get_light_rgbs(incident_light_dirs, device=device).to(device)

@@ -21,13 +21,24 @@ def Renderer_TensoIR_train(rays=None, normal_gt=None, light_idx=None, tensoIR=No
     if tensoIR.normals_kind == "gt_normals" and normal_gt is not None:
         normal_map = normal_gt.to(device)
     if is_relight and tensoIR.__dict__.get("_tir_static") is not None:
-        # shape-static variant (CUDA-graph capture): no compaction of the acc_mask rows.  Rays that miss get a zero
-        # normal for the secondary kernel (its cosine test then skips all their directions) and their shaded value
-        # is replaced by the white background afterwards, exactly as the scatter below does.
-        keep = acc_mask[:, None].to(normal_map.dtype)
-        shaded = render_with_BRDF(depth_map, normal_map * keep, albedo_map, roughness_map.repeat(1, 3), fresnel_map, rays, tensoIR, light_idx,
-                                  sample_method, chunk_size=chunk_size, device=device, args=args)
-        rgb_with_brdf = torch.where(acc_mask[:, None], shaded, torch.ones_like(rgb_map))
+        # shape-static variant (CUDA-graph capture): the acc_mask rows are compacted into a list of STATIC capacity
+        # (padding rows point at a dummy row N, carry a zero normal so the secondary kernel's cosine test skips all
+        # their directions, and are dropped by the scatter), exactly mirroring the dynamic branch below.
+        st = tensoIR.__dict__["_tir_static"]
+        n = rgb_map.shape[0]
+        cap = min(int(st.get("cap_hit", n)), n) if n > 0 else 0
+        idx = torch.nonzero_static(acc_mask, size=cap, fill_value=-1).reshape(-1)
+        real = idx >= 0
+        st["overflow"] += (acc_mask.sum() > cap).to(st["overflow"].dtype)
+        src = idx.clamp(min=0)
+        keep = real[:, None].to(normal_map.dtype)
+        shaded = render_with_BRDF(depth_map.index_select(0, src), normal_map.index_select(0, src) * keep,
+                                  albedo_map.index_select(0, src), roughness_map.index_select(0, src).repeat(1, 3),
+                                  fresnel_map.index_select(0, src), rays.index_select(0, src), tensoIR,
+                                  light_idx.index_select(0, src), sample_method, chunk_size=chunk_size, device=device,
+                                  args=args)
+        dst = torch.where(real, idx, torch.full_like(idx, n))
+        rgb_with_brdf = torch.ones((n + 1, 3), device=rgb_map.device, dtype=rgb_map.dtype).index_copy(0, dst, shaded)[:n]
     elif is_relight:
         masked = render_with_BRDF(depth_map[acc_mask], normal_map[acc_mask], albedo_map[acc_mask],
                                   roughness_map[acc_mask].repeat(1, 3), fresnel_map[acc_mask], rays[acc_mask],

@@ -42,14 +42,17 @@ class StaticTrainStep:
         """Size the static lists from eager marches over a few representative batches (max count x headroom)."""
         from . import primary
         self.model.__dict__.pop("_tir_static", None)
-        nv = na = 0
+        nv = na = nh = 0
         for rays, _ in batches:
             m = primary.march(self.model, rays.to(self.dev).float(), True, self.n_samples)
             nv = max(nv, int(m["xn"].shape[0]))
             na = max(na, int((m["weight"] > self.model.rayMarch_weight_thres).sum().item()))
+            acc = torch.zeros(rays.shape[0], device=self.dev).index_add_(0, m["ray_id"], m["weight"])
+            nh = max(nh, int((acc > 0.5).sum().item()))
         self.static["cap_valid"] = int(headroom * nv) + 4096
-        self.static["cap_app"] = int(headroom * na) + 4096
-        return self.static["cap_valid"], self.static["cap_app"]
+        self.static["cap_app"] = int(headroom * na) + 1024
+        self.static["cap_hit"] = min(self.n_rays, int(headroom * nh) + 64)
+        return self.static["cap_valid"], self.static["cap_app"], self.static["cap_hit"]
 
     # -- host side of one step: the reference's CPU draws, in the reference's order, into the static buffers
     def _stage_host_randoms(self):

@@ -37,7 +37,8 @@ def test_struct_sizes_match_header(lib):
 
 def test_null_arguments_are_rejected(lib):
     assert lib.tir_pack_channels_last(None, None, 1, 1, 1, None) == -1
-    assert lib.tir_density_points(None, None, 0, None, None, None) == -1
+    assert lib.tir_density_points(None, None, 5, None, None, None) == -1
+    assert lib.tir_density_points(None, None, 0, None, None, None) == 0      # empty input is a no-op, not an error
 
 
 def test_no_cpu_fallback():
