@@ -196,6 +196,22 @@ int tir_app_mlp_points_save(const TirField* field, const TirMlp* mlp, const floa
                             const int32_t* light_idx, int64_t n, int32_t act, float* out, float* save_xl,
                             float* save_in, float* save_h1, float* save_h2, void* stream);
 
+/* Shading epilogue of render_with_BRDF (models/relight_utils.py:452-475) with GGX_specular (:17-50):
+ *   rgb[i] = sum_l (albedo_i/pi + GGX_il) * (vis_il * direct[light_i][l] + indirect_il) * clamp(dir_l . n_i, 0) * weight_l
+ * normal/albedo/rough/fresnel/view [bs,3], light_idx [bs], dirs [n_dirs,3], weight [n_dirs] (solid angles),
+ * direct [n_lights,n_dirs,3] (SG environment light), vis [bs,n_dirs], indirect [bs,n_dirs,3] -> rgb [bs,3] (linear). */
+int tir_shade_fwd(const float* normal, const float* albedo, const float* rough, const float* fresnel,
+                  const float* view, const int32_t* light_idx, int64_t bs, const float* dirs, const float* weight,
+                  int32_t n_dirs, const float* direct, int32_t n_lights, const float* vis, const float* indirect,
+                  float* rgb, void* stream);
+/* analytic backward: g_rgb [bs,3] -> g_normal, g_albedo, g_rough, g_fresnel [bs,3] (overwritten) and g_direct
+ * [n_lights,n_dirs,3] (accumulated, caller zeroes). */
+int tir_shade_bwd(const float* normal, const float* albedo, const float* rough, const float* fresnel,
+                  const float* view, const int32_t* light_idx, int64_t bs, const float* dirs, const float* weight,
+                  int32_t n_dirs, const float* direct, int32_t n_lights, const float* vis, const float* indirect,
+                  const float* g_rgb, float* g_normal, float* g_albedo, float* g_rough, float* g_fresnel,
+                  float* g_direct, void* stream);
+
 /* ---- modular, autograd-facing half of the primary march (training needs gradients) --------------------- */
 
 /* plane*line products of the appearance tensors on normalised points: xn [n,3] -> out [n, 3*aC]

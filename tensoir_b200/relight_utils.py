@@ -104,8 +104,7 @@ def render_with_BRDF(depth_map, normal_map, albedo_map, roughness_map, fresnel_m
         incident_light_dirs = tensoIR.gen_light_incident_dirs(method=sample_method).to(device)   # host draws, ref order
     bs, nlights = surface_xyz.shape[0], incident_light_dirs.shape[0]
     surf2c = safe_l2_normalize(-rays_d, dim=-1)
-    surf2l = incident_light_dirs.reshape(1, -1, 3).expand(bs, -1, -1)
-    cosine = torch.clamp(torch.einsum("jk,ik->ij", incident_light_dirs, normal_map), min=0.0)
+    surf2l = cosine = None      # formed per (point, direction) inside the kernels
     # secondary rays: cosine test + 96-sample march + appearance MLP, generated on chip per (point, direction)
     with record_function("tir::secondary"):
         vis, indirect, _ = ops.secondary_radiance(
@@ -119,17 +118,16 @@ def render_with_BRDF(depth_map, normal_map, albedo_map, roughness_map, fresnel_m
 
 def _shade(tensoIR, normal_map, albedo_map, roughness_map, fresnel_map, surf2c, surf2l, cosine, vis, indirect,
            incident_light_dirs, light_idx, light_area_weight, nlights, sample_method, use_linear2srgb, device):
-    """Quadrature of the rendering equation, relight_utils.py:452-483."""
-    specular = GGX_specular(normal_map, surf2c, surf2l, roughness_map, fresnel_map)
-    surface_brdf = albedo_map.unsqueeze(1).expand(-1, nlights, -1) / np.pi + specular
-    envir_map_light_rgbs = tensoIR.get_light_rgbs(incident_light_dirs, device=device).to(device)
-    direct_light_rgbs = torch.index_select(envir_map_light_rgbs, dim=0, index=light_idx.reshape(-1).long())
-    light_rgbs = vis * direct_light_rgbs + indirect
+    """Quadrature of the rendering equation, relight_utils.py:452-483: fused CUDA kernel (forward + analytic
+    backward, csrc/tir_shade.cu); the SG light table stays in PyTorch (autograd reaches lgtSGs through it)."""
+    from .shade import shade
+    envir_map_light_rgbs = tensoIR.get_light_rgbs(incident_light_dirs, device=device).to(device)   # [L, nl, 3]
     if sample_method == 'stratifed_sample_equal_areas':
-        rgb_with_brdf = torch.mean(4 * torch.pi * surface_brdf * light_rgbs * cosine[:, :, None], dim=1)
+        weight = torch.full((nlights,), 4 * torch.pi / nlights, device=device)     # mean(4 pi x) over directions
     else:
-        rgb_with_brdf = torch.sum(surface_brdf * light_rgbs * cosine[:, :, None] * light_area_weight[None, :, None],
-                                  dim=1)
+        weight = light_area_weight
+    rgb_with_brdf = shade(normal_map, albedo_map, roughness_map, fresnel_map, envir_map_light_rgbs, surf2c, light_idx,
+                          incident_light_dirs, weight, vis, indirect)
     rgb_with_brdf = torch.clamp(rgb_with_brdf, min=0.0, max=1.0)
     if use_linear2srgb and rgb_with_brdf.shape[0] > 0:
         rgb_with_brdf = linear2srgb_torch(rgb_with_brdf)

@@ -398,3 +398,42 @@ def _oracle_sigma_dist(f, rays, n):
     xn = O.normalize_coord(f, pts)
     sigma[valid] = O.feature2density(f, O.density_feature(f, xn[valid]))
     return sigma, dists * f.distance_scale
+
+
+def test_fused_shade_kernel_vs_reference_math(golden_rotated):
+    """tir_shade_fwd/_bwd vs the reference's GGX + quadrature expressed in torch (the oracle's functions run on the
+    GPU) incl. every input gradient."""
+    from tensoir_b200.shade import shade
+    f = oracle_field(golden_rotated)
+    g = torch.Generator().manual_seed(3)
+    bs, nl, L = 37, 512, 2
+    nrm = torch.nn.functional.normalize(torch.randn(bs, 3, generator=g), dim=-1)
+    # roughness >= 0.25: below that GGX's nom0 = NoH^2 (alpha^2 - 1) + 1 cancels catastrophically near the specular
+    # peak and ANY two fp32 evaluation orders (also the reference's own CPU vs GPU) differ by ~1e-3 relative
+    alb, rough, fres = torch.rand(bs, 3, generator=g), torch.rand(bs, 1, generator=g).repeat(1, 3) * 0.74 + 0.25, \
+        torch.rand(bs, 3, generator=g) * 0.5
+    view = torch.nn.functional.normalize(torch.randn(bs, 3, generator=g), dim=-1)
+    direct = torch.rand(L, nl, 3, generator=g) * 2
+    vis, ind = torch.rand(bs, nl, 1, generator=g), torch.rand(bs, nl, 3, generator=g) * 0.3
+    li = (torch.arange(bs) % L).view(-1, 1)
+    torch.manual_seed(1)
+    dirs = O.gen_light_incident_dirs(f, 'stratified_sampling')
+    w = O.generate_envir_map_dir(16, 32)[0]
+    leaves = [t.clone().to(DEV).requires_grad_(True) for t in (nrm, alb, rough, fres, direct)]
+    leaves_ref = [t.clone().to(DEV).requires_grad_(True) for t in (nrm, alb, rough, fres, direct)]
+    cst = [t.to(DEV) for t in (view, li, dirs, w, vis, ind)]
+    got = shade(*leaves, cst[0], cst[1], cst[2], cst[3], cst[4], cst[5])
+    n_, a_, r_, f_, d_ = leaves_ref
+    surf2l = cst[2][None].expand(bs, -1, -1)
+    cos = torch.clamp(torch.einsum("ijk,ik->ij", surf2l, n_), min=0.0)
+    spec = O.ggx_specular(n_, cst[0], surf2l, r_, f_)
+    brdf = a_.unsqueeze(1) / torch.pi + spec
+    light = cst[4] * torch.index_select(d_, 0, cst[1].reshape(-1)) + cst[5]
+    want = torch.sum(brdf * light * cos[:, :, None] * cst[3][None, :, None], dim=1)
+    close(got, want, 5e-5, "shade fwd")
+    gw = torch.randn(bs, 3, generator=g).to(DEV)
+    (got * gw).sum().backward()
+    (want * gw).sum().backward()
+    for name, a, b in zip(("normal", "albedo", "rough", "fresnel", "direct"), leaves, leaves_ref):
+        scale = float(b.grad.abs().max()) + 1e-12
+        assert float((a.grad - b.grad).abs().max()) / scale < 5e-4, name
