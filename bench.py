@@ -35,7 +35,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=300)
     ap.add_argument("--batch", type=int, default=4096)
-    ap.add_argument("--cpu-rays", type=int, default=64, help="bounded CPU-baseline sample (primary rays / step)")
+    ap.add_argument("--cpu-rays", type=int, default=1024, help="bounded CPU-baseline sample (primary rays / step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="do not capture the step into a CUDA graph")
     return ap.parse_args()
@@ -111,8 +111,8 @@ def run_reference(a, rank, world):
     """The reference's own algorithm on the host CPU cores (oracle port), bounded sample per step."""
     if rank != 0:
         return
-    out = cpu_baseline(a, steps=a.steps, warmup=a.warmup)
-    line = {"metric": METRIC, "value": out["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+    out = cpu_baseline(a, steps=a.steps, warmup=a.warmup, budget_s=240.0)
+    line = {"metric": METRIC, "value": out["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": out["steps_done"],
             "warmup": a.warmup, "ms_per_step": out["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
             "config": workload_config(a, parallelism=f"cpu{out['cores']}"),
@@ -134,20 +134,46 @@ def workload_config(a, parallelism):
                   f"({'exceed' if a.grid >= 256 else 'fit in'} L2 at this grid)"}
 
 
-def cpu_baseline(a, steps=2, warmup=1):
-    """Oracle (port of the reference) fwd+bwd+Adam on a bounded sample of the same workload."""
+def _pick_threads(f, n_s):
+    """torch CPU ops on the oracle's small tensors get SLOWER past some thread count (on the 128-core GPU host a step
+    takes minutes at 128 threads); probe a few counts with one small secondary march each and keep the fastest -
+    i.e. all the threads the reference can actually use."""
     from oracle import tensoir_oracle as O
-    from helpers import named_oracle_params  # noqa: F401
+    cpu = os.cpu_count() or 1
+    cands = sorted({c for c in (cpu, 64, 32, 16, 8) if c <= cpu}, reverse=True)
+    g = torch.Generator().manual_seed(1)
+    pts = (torch.rand(4096, 3, generator=g) * 2 - 1) * 0.9
+    dirs = torch.nn.functional.normalize(torch.randn(4096, 3, generator=g), dim=-1)
+    li = torch.zeros(4096, 1, dtype=torch.int32)
+    best, probe = None, {}
+    for c in cands:
+        torch.set_num_threads(c)
+        O.compute_radiance(f, pts[:256], dirs[:256], li[:256], 96, 0.05, 1.5)          # warm
+        t0 = time.perf_counter()
+        O.compute_radiance(f, pts, dirs, li, 96, 0.05, 1.5)
+        probe[c] = time.perf_counter() - t0
+        if best is None or probe[c] < probe[best]:
+            best = c
+        if probe[c] > 20.0:          # hopeless setting, do not waste the budget on slower ones
+            continue
+    torch.set_num_threads(best)
+    return best, probe
+
+
+def cpu_baseline(a, steps=2, warmup=1, budget_s=120.0):
+    """Oracle (port of the reference) fwd+bwd+Adam on a bounded sample of the same workload, host cores only."""
+    from oracle import tensoir_oracle as O
     from tensoir_b200.synthetic import make_lego_state, hemisphere_poses, training_batch, n_samples_for
-    torch.set_num_threads(os.cpu_count() or 1)
-    cores = torch.get_num_threads()
+    torch.set_num_threads(min(os.cpu_count() or 1, 32))
     f = make_lego_state(a.grid)
+    n_s = n_samples_for(a.grid)
+    cores, probe = _pick_threads(f, n_s)
     for p in f.parameters():
         p.requires_grad_(True)
     opt = torch.optim.Adam([{"params": f.parameters(), "lr": 1e-3}], betas=(0.9, 0.99))
     poses = hemisphere_poses(100)
-    n_s = n_samples_for(a.grid)
-    rays_total, t_total = 0, 0.0
+    rays_total, t_total, done = 0, 0.0, 0
+    t_begin = time.perf_counter()
     for it in range(warmup + steps):
         rays, li = training_batch(poses, a.cpu_rays, it)
         f.counters.clear()
@@ -164,9 +190,14 @@ def cpu_baseline(a, steps=2, warmup=1):
         if it >= warmup:
             rays_total += a.cpu_rays + f.counters.get("secondary_rays", 0)
             t_total += dt
-    return {"value": rays_total / t_total, "ms_per_step": 1e3 * t_total / max(steps, 1), "cores": cores,
-            "sample": f"{a.cpu_rays} primary rays/step x {steps} steps of the same workload (oracle port, "
-                      f"torch CPU, {cores} threads)"}
+            done += 1
+        if time.perf_counter() - t_begin > budget_s and done >= 1:
+            break
+    return {"value": rays_total / t_total, "ms_per_step": 1e3 * t_total / max(done, 1), "cores": cores,
+            "steps_done": done,
+            "sample": f"{a.cpu_rays} primary rays/step x {done} steps of the same workload (oracle port, torch CPU, "
+                      f"{cores} of {os.cpu_count()} threads = fastest of the probed counts "
+                      f"{ {k: round(v, 2) for k, v in probe.items()} } s)"}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -246,6 +277,7 @@ def main():
         launches0 = _lib.launch_count
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.profiler.start()               # no-op unless a profiler is attached with --profile-from-start off
         e0.record()
         for rays, li in batches:
             loss = step(rays, li)
@@ -253,6 +285,7 @@ def main():
                 loss.item()                       # device -> host read of the step's result
         e1.record()
         barrier()
+        torch.cuda.profiler.stop()
         ms = e0.elapsed_time(e1)
         t = torch.tensor([ms], device=dev)
         if world > 1:
