@@ -803,3 +803,93 @@ def update_alpha_mask(f: OracleField, grid_size, thres=0.001):
     f.alpha_aabb = f.aabb.clone()
     valid = dense[alpha > 0.5]
     return torch.stack((valid.amin(0), valid.amax(0)))
+
+
+# ----------------------------------------------------------------------------------------
+# relighting pass (scripts/relight_importance.py) — "next" row (f)2 of SURVEY.md §8
+# ----------------------------------------------------------------------------------------
+class EnvLight:
+    """Environment_Light of relight_utils.py:110-205, built from arrays {name: [H,W,3] float32} instead of a
+    directory of .hdr files (read_hdr, relight_utils.py:598-611, is plain cv2 I/O)."""
+
+    def __init__(self, maps: dict, device='cpu'):
+        self.hdr_rgbs, self.hdr_pdf_sample, self.hdr_pdf_return, self.hdr_dir = {}, {}, {}, {}
+        for name, arr in maps.items():
+            rgb = torch.as_tensor(arr).float()
+            self.hdr_rgbs[name] = rgb.to(device)
+            inten = torch.sum(rgb, dim=2, keepdim=True)
+            H, W, _ = inten.shape
+            h_int = 1.0 / H
+            sin_t = torch.sin(torch.linspace(0 + 0.5 * h_int, np.pi - 0.5 * h_int, H))
+            pdf = inten * sin_t.view(-1, 1, 1)
+            pdf = pdf / torch.sum(pdf)
+            pdf_ret = pdf * H * W / (2 * np.pi * np.pi * sin_t.view(-1, 1, 1))
+            self.hdr_pdf_sample[name] = pdf.to(device)
+            self.hdr_pdf_return[name] = pdf_ret.to(device)
+            lat, lng = np.pi / H, 2 * np.pi / W
+            phi, theta = torch.meshgrid([torch.linspace(np.pi / 2 - 0.5 * lat, -np.pi / 2 + 0.5 * lat, H),
+                                         torch.linspace(np.pi - 0.5 * lng, -np.pi + 0.5 * lng, W)], indexing='ij')
+            dirs = torch.stack([torch.cos(theta) * torch.cos(phi), torch.sin(theta) * torch.cos(phi),
+                                torch.sin(phi)], dim=-1).view(H, W, 3)
+            self.hdr_dir[name] = dirs.to(device)
+
+    @torch.no_grad()
+    def sample_light(self, name, bs, num_samples, light_dir_idx=None):
+        """relight_utils.py:150-188 (importance branch).  ``light_dir_idx`` [bs,num_samples] replaces the multinomial
+        draw of :169 when given."""
+        pdf_s = self.hdr_pdf_sample[name].view(-1).expand(bs, -1)
+        pdf_r = self.hdr_pdf_return[name].view(-1).expand(bs, -1)
+        dirs = self.hdr_dir[name].view(-1, 3).expand(bs, -1, -1)
+        rgbs = self.hdr_rgbs[name].view(-1, 3).expand(bs, -1, -1)
+        if light_dir_idx is None:
+            light_dir_idx = torch.multinomial(pdf_s, num_samples, replacement=True)
+        ld = dirs.gather(1, light_dir_idx.unsqueeze(-1).expand(-1, -1, 3)).view(bs, num_samples, 3)
+        lr = rgbs.gather(1, light_dir_idx.unsqueeze(-1).expand(-1, -1, 3)).view(bs, num_samples, 3)
+        lp = pdf_r.gather(1, light_dir_idx).unsqueeze(-1)
+        return ld, lr, lp
+
+    def get_light(self, name, incident_dir):
+        """relight_utils.py:193-205."""
+        env = self.hdr_rgbs[name].permute(2, 0, 1).unsqueeze(0)
+        phi = torch.arccos(incident_dir[:, 2]).reshape(-1) - 1e-6
+        theta = torch.atan2(incident_dir[:, 1], incident_dir[:, 0]).reshape(-1)
+        qy = (phi / np.pi) * 2 - 1
+        qx = -theta / np.pi
+        grid = torch.stack((qx, qy)).permute(1, 0).unsqueeze(0).unsqueeze(0)
+        return F.grid_sample(env, grid, align_corners=True).squeeze().permute(1, 0).reshape(-1, 3)
+
+
+@torch.no_grad()
+def relight_chunk(f: OracleField, env: EnvLight, name, rays, maps, rescale_value, light_dir_idx=None,
+                  num_samples=512, acc_thres=0.5, vis_equation='nerv'):
+    """Per-chunk body of relight(), scripts/relight_importance.py:99-181.  ``maps`` = (depth, normal, albedo,
+    roughness, fresnel, acc) of the primary march for ``rays``.  -> (with_bg, without_bg) [n,3]."""
+    depth, normal, albedo, rough, fresnel, acc = maps
+    dev = rays.device
+    relight_rgb = torch.ones((rays.shape[0], 3), device=dev)
+    mask = acc > acc_thres
+    rays_o, rays_d = rays[:, :3], rays[:, 3:]
+    surf = (rays_o + depth.unsqueeze(-1) * rays_d)[mask]
+    m_n, m_a, m_r, m_f = normal[mask], albedo[mask], rough[mask], fresnel[mask]
+    surf2l, l_rgb, l_pdf = env.sample_light(name, m_n.shape[0], num_samples, light_dir_idx)
+    surf2c = safe_l2_normalize(-rays_d[mask], dim=-1)
+    cosine = torch.einsum("ijk,ik->ij", surf2l, m_n)
+    cmask = cosine > 1e-6
+    vis = torch.zeros((*cmask.shape, 1), device=dev)
+    pts = surf[:, None, :].expand((*cmask.shape, 3))[cmask]
+    nerv, nerf = compute_transmittance(f, pts, surf2l[cmask], 96, 0.05, 1.5)
+    vis[cmask] = (nerv if vis_equation == 'nerv' else nerf).unsqueeze(-1)
+    spec = ggx_specular(m_n, surf2c, surf2l, m_r, m_f)
+    brdf = (m_a * rescale_value).unsqueeze(1).expand(-1, surf2l.shape[1], -1) / np.pi + spec
+    contrib = brdf * (vis * l_rgb) * cosine[:, :, None] / l_pdf
+    srgb = torch.clamp(torch.mean(contrib, dim=1), min=0.0, max=1.0)
+    if srgb.shape[0] > 0:
+        srgb = linear2srgb(srgb)
+    relight_rgb[mask] = srgb
+    bg = linear2srgb(torch.clamp(env.get_light(name, rays_d), min=0.0, max=1.0))
+    without_bg = torch.ones_like(bg)
+    without_bg[mask] = relight_rgb[mask]
+    acc_t = acc[..., None].clone()
+    acc_t[acc_t <= 0.9] = 0.0
+    with_bg = acc_t * without_bg + (1.0 - acc_t) * bg
+    return with_bg, without_bg

@@ -202,6 +202,48 @@ def main():
     # number of app samples = rows of the randn draw; recover it by replaying the oracle in the test instead.
     fx["train_seed"] = 77
     fx["train_jitter"] = jit
+    # g) relighting pass (scripts/relight_importance.py:99-181) with the reference's Environment_Light on a synthetic
+    #    Radiance .hdr (log-normal radiance + a sun disc), multinomial draws recorded
+    import cv2, tempfile
+    rs = np.random.RandomState(7)
+    envmap = np.exp(rs.normal(-1.0, 0.6, size=(16, 32, 3))).astype(np.float32)
+    envmap[3:5, 20:22] += 40.0
+    tmpd = tempfile.mkdtemp()
+    cv2.imwrite(os.path.join(tmpd, "sunny.hdr"), cv2.cvtColor(envmap, cv2.COLOR_RGB2BGR))
+    env = ru.Environment_Light(tmpd, device='cpu')
+    fx["env_rgb"] = env.hdr_rgbs["sunny"].clone()
+    fx["env_pdf_sample"], fx["env_pdf_return"] = env.hdr_pdf_sample["sunny"].clone(), env.hdr_pdf_return["sunny"].clone()
+    fx["env_dir"] = env.hdr_dir["sunny"].clone()
+    torch.manual_seed(31)
+    with torch.enable_grad():
+        prim = m(rays, light_idx, is_train=False, white_bg=True, ndc_ray=False, N_samples=-1)
+    rgb_c, depth_c, normal_c, albedo_c, rough_c, fresnel_c, acc_c = [t.detach() for t in prim[:7]]
+    amask = acc_c > 0.5
+    torch.manual_seed(32)
+    ldir, lrgb, lpdf = env.sample_light("sunny", int(amask.sum()), 64)
+    torch.manual_seed(32)
+    fx["relight_idx"] = torch.multinomial(env.hdr_pdf_sample["sunny"].view(-1).expand(int(amask.sum()), -1), 64,
+                                          replacement=True)
+    surf2c = ru.safe_l2_normalize(-rays[:, 3:][amask], dim=-1)
+    cosine = torch.einsum("ijk,ik->ij", ldir, normal_c[amask])
+    cmask = cosine > 1e-6
+    vis = torch.zeros((*cmask.shape, 1))
+    surf = (rays[:, :3] + depth_c.unsqueeze(-1) * rays[:, 3:])[amask]
+    nerv, nerf = ru.compute_transmittance(tensoIR=m, surf_pts=surf[:, None, :].expand((*cmask.shape, 3))[cmask],
+                                          light_in_dir=ldir[cmask], nSample=96, vis_near=0.05, vis_far=1.5)
+    vis[cmask] = nerv.unsqueeze(-1)
+    spec = ru.brdf_specular(normal_c[amask], surf2c, ldir, rough_c[amask].repeat(1, 3), fresnel_c[amask])
+    brdf = (albedo_c[amask] * 1.7).unsqueeze(1).expand(-1, 64, -1) / np.pi + spec
+    srgb = torch.clamp(torch.mean(brdf * (vis * lrgb) * cosine[:, :, None] / lpdf, dim=1), min=0.0, max=1.0)
+    srgb = ru.linear2srgb_torch(srgb)
+    bg = ru.linear2srgb_torch(torch.clamp(env.get_light("sunny", rays[:, 3:]), min=0.0, max=1.0))
+    wo = torch.ones_like(bg)
+    wo[amask] = srgb
+    acc_t = acc_c[..., None].clone()
+    acc_t[acc_t <= 0.9] = 0.0
+    fx["relight_maps"] = (depth_c, normal_c, albedo_c, rough_c.repeat(1, 3), fresnel_c, acc_c)
+    fx["relight_with_bg"], fx["relight_without_bg"] = acc_t * wo + (1.0 - acc_t) * bg, wo
+    fx["relight_bg_lookup"] = env.get_light("sunny", rays[:, 3:]).clone()
     out["rotated"] = fx
     torch.save(fx, os.path.join(HERE, "rotated_g24.pt"))
 

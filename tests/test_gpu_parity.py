@@ -437,3 +437,23 @@ def test_fused_shade_kernel_vs_reference_math(golden_rotated):
     for name, a, b in zip(("normal", "albedo", "rough", "fresnel", "direct"), leaves, leaves_ref):
         scale = float(b.grad.abs().max()) + 1e-12
         assert float((a.grad - b.grad).abs().max()) / scale < 5e-4, name
+
+
+def test_relight_chunk(golden_rotated):
+    """scripts/relight_importance.py chunk body through the fused density march, with the reference's recorded
+    multinomial indices; plus one full relight_view with the inverse-CDF sampler (finite, in range, deterministic
+    background)."""
+    from tensoir_b200.relight import Environment_Light, relight_chunk, relight_view
+    fx = golden_rotated
+    m = model_from_fixture(fx, DEV)
+    env = Environment_Light({"sunny": fx["env_rgb"].numpy()}, device=DEV)
+    maps = tuple(t.to(DEV) for t in fx["relight_maps"])
+    w, wo = relight_chunk(m, env, "sunny", fx["rays"].to(DEV), maps, 1.7, fx["relight_idx"].to(DEV), 64)
+    close(wo, fx["relight_without_bg"], TOL, "relight without bg")
+    close(w, fx["relight_with_bg"], TOL, "relight with bg")
+    torch.manual_seed(3)
+    res = relight_view(m, env, ["sunny"], fx["rays"].to(DEV), batch_size=40, num_samples=128)
+    wv, wov = res["sunny"]
+    assert wv.shape == (64, 3) and torch.isfinite(wv).all() and float(wv.min()) >= 0 and float(wv.max()) <= 1
+    miss = res["_primary"][5] <= 0.5
+    assert torch.equal(wov[miss], torch.ones_like(wov[miss]))

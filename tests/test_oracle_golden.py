@@ -143,3 +143,18 @@ def test_update_alpha_mask(golden_rotated):
     new_aabb = O.update_alpha_mask(f, (24, 24, 24))
     eq(f.alpha_volume, fx["alpha_volume"])
     eq(new_aabb, fx["new_aabb"])
+
+
+def test_relight_pass(golden_rotated):
+    """Environment_Light tables, background lookup and the per-chunk relighting math of scripts/relight_importance.py
+    (with the reference's recorded multinomial indices)."""
+    fx = golden_rotated
+    f = oracle_field(fx)
+    env = O.EnvLight({"sunny": fx["env_rgb"]})
+    eq(env.hdr_pdf_sample["sunny"], fx["env_pdf_sample"])
+    eq(env.hdr_pdf_return["sunny"], fx["env_pdf_return"])
+    eq(env.hdr_dir["sunny"], fx["env_dir"])
+    eq(env.get_light("sunny", fx["rays"][:, 3:]), fx["relight_bg_lookup"])
+    w, wo = O.relight_chunk(f, env, "sunny", fx["rays"], fx["relight_maps"], 1.7, fx["relight_idx"], 64)
+    eq(wo, fx["relight_without_bg"])
+    eq(w, fx["relight_with_bg"])
