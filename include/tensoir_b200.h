@@ -245,10 +245,13 @@ int tir_valid_samples_fill(const TirField* field, const float* rays_o, const flo
  * weight[i] = alpha_i * T_i, trans[i] = T_i (exclusive), t_last[ray]. */
 int tir_composite_fwd(const float* sigma, const float* dist, const int64_t* offsets, int64_t n_rays,
                       float distance_scale, float* weight, float* trans, float* t_last,
-                      int64_t limit /* 0 = none; list rows >= limit are ignored */, void* stream);
+                      int64_t limit /* 0 = none; list rows >= limit are ignored */,
+                      const float* z /* [n_valid] or NULL */, float* acc /* [n_rays] sum w, or NULL */,
+                      float* depth /* [n_rays] sum w*z, or NULL */, void* stream);
 int tir_composite_bwd(const float* sigma, const float* dist, const int64_t* offsets, int64_t n_rays,
                       float distance_scale, const float* weight, const float* trans, const float* g_weight,
-                      float* g_sigma, int64_t limit, void* stream);
+                      float* g_sigma, int64_t limit, const float* z, const float* g_acc /* [n_rays] or NULL */,
+                      const float* g_depth /* [n_rays] or NULL */, void* stream);
 
 #ifdef __cplusplus
 }

@@ -95,9 +95,9 @@ EXPORTS = {
     "tir_valid_samples_fill": (C.c_int, [C.POINTER(TirField), f32p, f32p, C.c_int64, C.POINTER(TirMarchCfg),
                                          C.c_void_p, C.c_void_p, C.c_void_p, f32p, f32p, f32p, C.c_int64, C.c_void_p]),
     "tir_composite_fwd": (C.c_int, [f32p, f32p, C.c_void_p, C.c_int64, C.c_float, f32p, f32p, f32p, C.c_int64,
-                                    C.c_void_p]),
+                                    f32p, f32p, f32p, C.c_void_p]),
     "tir_composite_bwd": (C.c_int, [f32p, f32p, C.c_void_p, C.c_int64, C.c_float, f32p, f32p, f32p, f32p,
-                                    C.c_int64, C.c_void_p]),
+                                    C.c_int64, f32p, f32p, f32p, C.c_void_p]),
 }
 
 # kernels launched per entry point (for bench.py's gpu_launches claim)

@@ -332,37 +332,46 @@ __global__ void valid_samples_kernel(TirField f, TirMarchCfg cfg, const float* _
 __global__ void composite_fwd_kernel(const float* __restrict__ sigma, const float* __restrict__ dist,
                                      const int64_t* __restrict__ offsets, int64_t n_rays, float scale,
                                      float* __restrict__ weight, float* __restrict__ trans,
-                                     float* __restrict__ t_last, int64_t limit) {
+                                     float* __restrict__ t_last, int64_t limit, const float* __restrict__ z,
+                                     float* __restrict__ acc, float* __restrict__ depth) {
   const int64_t ray = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (ray >= n_rays) return;
-  float T = 1.f;
+  float T = 1.f, a = 0.f, d = 0.f;
   const int64_t e_ = offsets[ray + 1] < limit ? offsets[ray + 1] : limit;
   for (int64_t i = offsets[ray]; i < e_; ++i) {
     const float alpha = __fsub_rn(1.f, expf(__fmul_rn(-sigma[i], __fmul_rn(dist[i], scale))));
-    weight[i] = __fmul_rn(alpha, T);
+    const float w = __fmul_rn(alpha, T);
+    weight[i] = w;
     trans[i] = T;
+    a += w;
+    if (z) d = fmaf(w, z[i], d);
     T = __fmul_rn(T, __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f));
   }
   if (t_last) t_last[ray] = T;
+  if (acc) acc[ray] = a;                 // acc_map = sum_s weight          (tensorBase:974)
+  if (depth) depth[ray] = d;             // depth_map = sum_s weight * z    (tensorBase:975)
 }
 
 __global__ void composite_bwd_kernel(const float* __restrict__ sigma, const float* __restrict__ dist,
                                      const int64_t* __restrict__ offsets, int64_t n_rays, float scale,
                                      const float* __restrict__ weight, const float* __restrict__ trans,
                                      const float* __restrict__ g_weight, float* __restrict__ g_sigma,
-                                     int64_t limit) {
+                                     int64_t limit, const float* __restrict__ z, const float* __restrict__ g_acc,
+                                     const float* __restrict__ g_depth) {
   const int64_t ray = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (ray >= n_rays) return;
   const int64_t b = offsets[ray], e = offsets[ray + 1] < limit ? offsets[ray + 1] : limit;
   float suffix = 0.f;   // sum_{j>i} g_j * w_j
+  const float ga = g_acc ? g_acc[ray] : 0.f, gd = (g_depth && z) ? g_depth[ray] : 0.f;
   for (int64_t i = e - 1; i >= b; --i) {
     const float d = dist[i] * scale;
     const float ex = expf(-sigma[i] * d);
     const float alpha = 1.f - ex;
     const float om = (1.f - alpha) + 1e-10f;
-    const float g_alpha = g_weight[i] * trans[i] - suffix / om;
+    const float gw = (g_weight ? g_weight[i] : 0.f) + ga + (z ? gd * z[i] : 0.f);   // d/d weight_i incl. acc / depth
+    const float g_alpha = gw * trans[i] - suffix / om;
     g_sigma[i] = g_alpha * d * ex;
-    suffix += g_weight[i] * weight[i];
+    suffix += gw * weight[i];
   }
 }
 
@@ -463,23 +472,25 @@ extern "C" int tir_valid_samples_fill(const TirField* field, const float* rays_o
 
 extern "C" int tir_composite_fwd(const float* sigma, const float* dist, const int64_t* offsets, int64_t n_rays,
                                  float distance_scale, float* weight, float* trans, float* t_last, int64_t limit,
-                                 void* stream) {
+                                 const float* z, float* acc, float* depth, void* stream) {
   if (n_rays <= 0) return TIR_OK;   // empty input: nothing to do (pointers of empty tensors are NULL)
   if (!sigma || !dist || !offsets || !weight || !trans) return TIR_ERR_NULL;
   if (n_rays <= 0) return TIR_OK;
   composite_fwd_kernel<<<(unsigned)((n_rays + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-      sigma, dist, offsets, n_rays, distance_scale, weight, trans, t_last, limit > 0 ? limit : (int64_t)1 << 62);
+      sigma, dist, offsets, n_rays, distance_scale, weight, trans, t_last, limit > 0 ? limit : (int64_t)1 << 62, z, acc,
+      depth);
   return (int)cudaGetLastError();
 }
 
 extern "C" int tir_composite_bwd(const float* sigma, const float* dist, const int64_t* offsets, int64_t n_rays,
                                  float distance_scale, const float* weight, const float* trans,
-                                 const float* g_weight, float* g_sigma, int64_t limit, void* stream) {
+                                 const float* g_weight, float* g_sigma, int64_t limit, const float* z,
+                                 const float* g_acc, const float* g_depth, void* stream) {
   if (n_rays <= 0) return TIR_OK;   // empty input: nothing to do (pointers of empty tensors are NULL)
-  if (!sigma || !dist || !offsets || !weight || !trans || !g_weight || !g_sigma) return TIR_ERR_NULL;
+  if (!sigma || !dist || !offsets || !weight || !trans || !g_sigma) return TIR_ERR_NULL;
   if (n_rays <= 0) return TIR_OK;
   composite_bwd_kernel<<<(unsigned)((n_rays + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
       sigma, dist, offsets, n_rays, distance_scale, weight, trans, g_weight, g_sigma,
-      limit > 0 ? limit : (int64_t)1 << 62);
+      limit > 0 ? limit : (int64_t)1 << 62, z, g_acc, g_depth);
   return (int)cudaGetLastError();
 }

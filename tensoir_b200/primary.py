@@ -71,8 +71,8 @@ def march(model, rays, is_train, n_samples, counters=None):
         sigma = model.feature2density(feat)
     else:
         sigma = torch.zeros(0, device=rays.device)
-    weight, t_last = vm.composite(sigma, lst["dist"], lst["offsets"], model.distance_scale)
-    lst.update(ray_id=ray_id, sigma=sigma, weight=weight, t_last=t_last)
+    weight, t_last, acc, depth = vm.composite(sigma, lst["dist"], lst["offsets"], model.distance_scale, lst["z"])
+    lst.update(ray_id=ray_id, sigma=sigma, weight=weight, t_last=t_last, acc=acc, depth=depth)
     return lst
 
 
@@ -113,8 +113,7 @@ def _forward_relight_tail(model, rays, light_idx, white_bg, is_train, is_relight
     r_a = ray_id.index_select(0, app_idx)
     x_a = xn.index_select(0, app_idx)
 
-    acc_map = _segment_sum(weight, ray_id, n_rays)
-    depth_map = _segment_sum(weight * m["z"], ray_id, n_rays)
+    acc_map, depth_map = m["acc"], m["depth"]           # per-ray sums straight from the compositing kernel
 
     z3 = torch.zeros(n_rays, 3, device=dev)
     z1 = torch.zeros(n_rays, 1, device=dev)
@@ -198,7 +197,7 @@ def forward_init(model, rays_chunk, white_bg=True, is_train=False, N_samples=-1)
     m = march(model, rays, is_train, N_samples, counters=model.__dict__.get("_tir_counters"))
     ray_id, weight, xn = m["ray_id"], m["weight"], m["xn"]
     app_idx = torch.nonzero(weight > model.rayMarch_weight_thres).reshape(-1)
-    acc_map = _segment_sum(weight, ray_id, n_rays)
+    acc_map = m["acc"]
     rgb_map = torch.zeros(n_rays, 3, device=rays.device)
     if app_idx.shape[0] > 0:
         r_a = ray_id.index_select(0, app_idx)
@@ -209,6 +208,5 @@ def forward_init(model, rays_chunk, white_bg=True, is_train=False, N_samples=-1)
         rgb_map = rgb_map + (1. - acc_map[..., None])
     rgb_map = rgb_map.clamp(0, 1)
     with torch.no_grad():
-        depth_map = _segment_sum(weight * m["z"], ray_id, n_rays)
-        depth_map = depth_map + (1. - acc_map) * rays[..., -1]
+        depth_map = m["depth"].detach() + (1. - acc_map) * rays[..., -1]
     return rgb_map, depth_map

@@ -47,8 +47,7 @@ class StaticTrainStep:
             m = primary.march(self.model, rays.to(self.dev).float(), True, self.n_samples)
             nv = max(nv, int(m["xn"].shape[0]))
             na = max(na, int((m["weight"] > self.model.rayMarch_weight_thres).sum().item()))
-            acc = torch.zeros(rays.shape[0], device=self.dev).index_add_(0, m["ray_id"], m["weight"])
-            nh = max(nh, int((acc > 0.5).sum().item()))
+            nh = max(nh, int((m["acc"] > 0.5).sum().item()))
         self.static["cap_valid"] = int(headroom * nv) + 4096
         self.static["cap_app"] = int(headroom * na) + 1024
         self.static["cap_hit"] = min(self.n_rays, int(headroom * nh) + 64)

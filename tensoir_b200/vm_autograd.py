@@ -152,37 +152,44 @@ def app_products(model, xn):
 
 class _Composite(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, sigma, dist, offsets, scale):
+    def forward(ctx, sigma, dist, offsets, scale, z):
         lib = _lib.load()
         sigma = sigma.contiguous()
         n_rays = offsets.numel() - 1
         weight = torch.zeros_like(sigma)      # rows of a static-capacity list past the real total stay 0
         trans = torch.zeros_like(sigma)
         t_last = torch.empty(n_rays, device=sigma.device)
+        acc = torch.empty(n_rays, device=sigma.device)
+        depth = torch.empty(n_rays, device=sigma.device)
         _lib.check(lib.tir_composite_fwd(_lib.dptr(sigma), _lib.dptr(dist), _lib.dptr(offsets, torch.int64), n_rays,
                                          float(scale), _lib.dptr(weight), _lib.dptr(trans), _lib.dptr(t_last),
-                                         sigma.numel(), _lib.stream_ptr()), "tir_composite_fwd")
-        ctx.save_for_backward(sigma, dist, offsets, weight, trans)
+                                         sigma.numel(), _lib.dptr(z), _lib.dptr(acc), _lib.dptr(depth),
+                                         _lib.stream_ptr()), "tir_composite_fwd")
+        ctx.save_for_backward(sigma, dist, offsets, weight, trans, z)
         ctx.scale = float(scale)
         ctx.mark_non_differentiable(t_last)
-        return weight, t_last
+        return weight, t_last, acc, depth
 
     @staticmethod
-    def backward(ctx, g_weight, _g_t):
-        sigma, dist, offsets, weight, trans = ctx.saved_tensors
+    def backward(ctx, g_weight, _g_t, g_acc, g_depth):
+        sigma, dist, offsets, weight, trans, z = ctx.saved_tensors
         lib = _lib.load()
-        g_weight = g_weight.contiguous().float()
+        nul = C.c_void_p(0)
+
+        def ptr(t):
+            return nul if t is None else _lib.dptr(t.contiguous().float())
         g_sigma = torch.zeros_like(sigma)
         _lib.check(lib.tir_composite_bwd(_lib.dptr(sigma), _lib.dptr(dist), _lib.dptr(offsets, torch.int64),
                                          offsets.numel() - 1, ctx.scale, _lib.dptr(weight), _lib.dptr(trans),
-                                         _lib.dptr(g_weight), _lib.dptr(g_sigma), sigma.numel(), _lib.stream_ptr()),
-                   "tir_composite_bwd")
-        return g_sigma, None, None, None
+                                         ptr(g_weight), _lib.dptr(g_sigma), sigma.numel(), _lib.dptr(z),
+                                         ptr(g_acc), ptr(g_depth), _lib.stream_ptr()), "tir_composite_bwd")
+        return g_sigma, None, None, None, None
 
 
-def composite(sigma, dist, offsets, scale):
-    """raw2alpha over ray segments (tensorBase:21-28) -> (weight [n_valid], T_last [n_rays])."""
-    return _Composite.apply(sigma, dist, offsets, scale)
+def composite(sigma, dist, offsets, scale, z):
+    """raw2alpha over ray segments (tensorBase:21-28) + the two per-ray sums that need every valid sample
+    (acc_map, depth_map, tensorBase:974-975) -> (weight [n_valid], T_last [n_rays], acc [n_rays], depth [n_rays])."""
+    return _Composite.apply(sigma, dist, offsets, scale, z)
 
 
 def valid_samples(model, rays_o, rays_d, *, n_samples=-1, jitter=None, table=None, counters=None, no_bbox=False,
