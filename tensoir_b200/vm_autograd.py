@@ -158,13 +158,14 @@ class _Composite(torch.autograd.Function):
         n_rays = offsets.numel() - 1
         weight = torch.zeros_like(sigma)      # rows of a static-capacity list past the real total stay 0
         trans = torch.zeros_like(sigma)
-        t_last = torch.empty(n_rays, device=sigma.device)
-        acc = torch.empty(n_rays, device=sigma.device)
-        depth = torch.empty(n_rays, device=sigma.device)
-        _lib.check(lib.tir_composite_fwd(_lib.dptr(sigma), _lib.dptr(dist), _lib.dptr(offsets, torch.int64), n_rays,
-                                         float(scale), _lib.dptr(weight), _lib.dptr(trans), _lib.dptr(t_last),
-                                         sigma.numel(), _lib.dptr(z), _lib.dptr(acc), _lib.dptr(depth),
-                                         _lib.stream_ptr()), "tir_composite_fwd")
+        t_last = torch.ones(n_rays, device=sigma.device)
+        acc = torch.zeros(n_rays, device=sigma.device)
+        depth = torch.zeros(n_rays, device=sigma.device)
+        if sigma.numel() > 0:        # a chunk whose rays all miss the aabb has no valid sample at all
+            _lib.check(lib.tir_composite_fwd(_lib.dptr(sigma), _lib.dptr(dist), _lib.dptr(offsets, torch.int64),
+                                             n_rays, float(scale), _lib.dptr(weight), _lib.dptr(trans),
+                                             _lib.dptr(t_last), sigma.numel(), _lib.dptr(z), _lib.dptr(acc),
+                                             _lib.dptr(depth), _lib.stream_ptr()), "tir_composite_fwd")
         ctx.save_for_backward(sigma, dist, offsets, weight, trans, z)
         ctx.scale = float(scale)
         ctx.mark_non_differentiable(t_last)
@@ -179,10 +180,11 @@ class _Composite(torch.autograd.Function):
         def ptr(t):
             return nul if t is None else _lib.dptr(t.contiguous().float())
         g_sigma = torch.zeros_like(sigma)
-        _lib.check(lib.tir_composite_bwd(_lib.dptr(sigma), _lib.dptr(dist), _lib.dptr(offsets, torch.int64),
-                                         offsets.numel() - 1, ctx.scale, _lib.dptr(weight), _lib.dptr(trans),
-                                         ptr(g_weight), _lib.dptr(g_sigma), sigma.numel(), _lib.dptr(z),
-                                         ptr(g_acc), ptr(g_depth), _lib.stream_ptr()), "tir_composite_bwd")
+        if sigma.numel() > 0:
+            _lib.check(lib.tir_composite_bwd(_lib.dptr(sigma), _lib.dptr(dist), _lib.dptr(offsets, torch.int64),
+                                             offsets.numel() - 1, ctx.scale, _lib.dptr(weight), _lib.dptr(trans),
+                                             ptr(g_weight), _lib.dptr(g_sigma), sigma.numel(), _lib.dptr(z),
+                                             ptr(g_acc), ptr(g_depth), _lib.stream_ptr()), "tir_composite_bwd")
         return g_sigma, None, None, None, None
 
 

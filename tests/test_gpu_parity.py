@@ -378,6 +378,13 @@ def test_edge_cases(golden_rotated):
     for k, w in want.items():
         close(got[k], w, TOL, k)
     assert float(got["acc_map"][0]) == 0.0            # the ray that leaves the scene composites nothing
+    # (ii-b) a chunk in which EVERY ray misses the aabb (image corners of a full-view render): no valid sample at all
+    away = torch.cat([o[:1].repeat(5, 1), d[:1].repeat(5, 1)], 1)
+    with torch.no_grad():
+        g2 = Renderer_TensoIR_train(away, None, torch.zeros(5, 1, dtype=torch.int32), m, N_samples=-1,
+                                    is_train=False, is_relight=True, device=DEV, args=args)
+    assert torch.equal(g2["acc_map"].cpu(), torch.zeros(5)) and torch.equal(g2["rgb_with_brdf_map"].cpu(),
+                                                                            torch.ones(5, 3))
     # (iii) no alpha mask, one sample per ray
     m2 = model_from_fixture(fx, DEV, with_mask=False)
     f2 = oracle_field(fx, with_mask=False)
