@@ -56,37 +56,29 @@ class TensorVMSplit(TensorBase):
             grad_vars += [{'params': self.renderModule_normal.parameters(), 'lr': lr_init_network}]
         return grad_vars
 
-    # ---- regularisers (parameter-only; tensoRF_rotated_lights.py:60-92) -----------------
+    # ---- regularisers (parameter-only, same values as tensoRF_rotated_lights.py:60-92) --------------
+    @staticmethod
+    def _offdiag_gram_mean(line):
+        """mean |<v_i, v_j>|, i != j, over the components of one line factor [1,C,D,1] (the 'Ortho' term)."""
+        v = line.reshape(line.shape[1], line.shape[2])
+        gram = v @ v.t()
+        off = ~torch.eye(gram.shape[0], dtype=torch.bool, device=gram.device)
+        return gram[off].abs().mean()
+
     def vectorDiffs(self, vector_comps):
-        total = 0
-        for idx in range(len(vector_comps)):
-            n_comp, n_size = vector_comps[idx].shape[1:-1]
-            v = vector_comps[idx].view(n_comp, n_size)
-            dotp = torch.matmul(v, v.transpose(-1, -2))
-            non_diagonal = dotp.view(-1)[1:].view(n_comp - 1, n_comp + 1)[..., :-1]
-            total = total + torch.mean(torch.abs(non_diagonal))
-        return total
+        return sum(self._offdiag_gram_mean(v) for v in vector_comps)
 
     def vector_comp_diffs(self):
         return self.vectorDiffs(self.density_line) + self.vectorDiffs(self.app_line)
 
     def density_L1(self):
-        total = 0
-        for idx in range(len(self.density_plane)):
-            total = total + torch.mean(torch.abs(self.density_plane[idx])) + torch.mean(torch.abs(self.density_line[idx]))
-        return total
+        return sum(p.abs().mean() + l.abs().mean() for p, l in zip(self.density_plane, self.density_line))
 
     def TV_loss_density(self, reg):
-        total = 0
-        for idx in range(len(self.density_plane)):
-            total = total + reg(self.density_plane[idx]) * 1e-2
-        return total
+        return sum(reg(p) * 1e-2 for p in self.density_plane)
 
     def TV_loss_app(self, reg):
-        total = 0
-        for idx in range(len(self.app_plane)):
-            total = total + reg(self.app_plane[idx]) * 1e-2
-        return total
+        return sum(reg(p) * 1e-2 for p in self.app_plane)
 
     # ---- VM gathers (kernel-backed, differentiable w.r.t. the factors) -------------------
     def compute_densityfeature(self, xyz_sampled):
@@ -124,49 +116,46 @@ class TensorVMSplit(TensorBase):
         prod = vm_autograd.app_products(self, xyz_sampled)
         return self.basis_mat(prod * self._light_rows(light_idx, prod.shape[0]))
 
-    # ---- grid maintenance (tensoRF_rotated_lights.py:226-288) ---------------------------
+    # ---- grid maintenance (behaviour of tensoRF_rotated_lights.py:226-288) ---------------------------------
+    # Both operations REBIND the Parameters (the train loop rebuilds Adam afterwards, train_tensoIR.py:421-422);
+    # DeviceField notices the new (data_ptr, version, shape) and rebuilds the kernel-side shadows.
+    def _rebind(self, plist, k, tensor):
+        plist[k] = torch.nn.Parameter(tensor)
+
     @torch.no_grad()
     def up_sampling_VM(self, plane_coef, line_coef, res_target):
-        for i in range(len(self.vecMode)):
-            vec_id = self.vecMode[i]
-            mat_id_0, mat_id_1 = self.matMode[i]
-            plane_coef[i] = torch.nn.Parameter(F.interpolate(plane_coef[i].data,
-                                                             size=(res_target[mat_id_1], res_target[mat_id_0]),
-                                                             mode='bilinear', align_corners=True))
-            line_coef[i] = torch.nn.Parameter(F.interpolate(line_coef[i].data, size=(res_target[vec_id], 1),
-                                                            mode='bilinear', align_corners=True))
+        for k, (m, v) in enumerate(zip(self.matMode, self.vecMode)):
+            size_plane = (res_target[m[1]], res_target[m[0]])
+            self._rebind(plane_coef, k, F.interpolate(plane_coef[k].data, size=size_plane, mode='bilinear',
+                                                      align_corners=True))
+            self._rebind(line_coef, k, F.interpolate(line_coef[k].data, size=(res_target[v], 1), mode='bilinear',
+                                                     align_corners=True))
         return plane_coef, line_coef
 
     @torch.no_grad()
     def upsample_volume_grid(self, res_target):
-        self.app_plane, self.app_line = self.up_sampling_VM(self.app_plane, self.app_line, res_target)
-        self.density_plane, self.density_line = self.up_sampling_VM(self.density_plane, self.density_line, res_target)
+        for planes, lines in ((self.app_plane, self.app_line), (self.density_plane, self.density_line)):
+            self.up_sampling_VM(planes, lines, res_target)
         self.update_stepSize(res_target)
         print(f'upsamping to {res_target}')
 
     @torch.no_grad()
     def shrink(self, new_aabb):
+        """Crop every factor to the voxel range covering ``new_aabb`` and snap the aabb to that range when the
+        alpha-mask resolution differs from the grid's."""
         print("====> shrinking ...")
-        xyz_min, xyz_max = new_aabb
-        t_l, b_r = (xyz_min - self.aabb[0]) / self.units, (xyz_max - self.aabb[0]) / self.units
-        t_l, b_r = torch.round(torch.round(t_l)).long(), torch.round(b_r).long() + 1
-        b_r = torch.stack([b_r, self.gridSize]).amin(0)
-        for i in range(len(self.vecMode)):
-            mode0 = self.vecMode[i]
-            self.density_line[i] = torch.nn.Parameter(self.density_line[i].data[..., t_l[mode0]:b_r[mode0], :])
-            self.app_line[i] = torch.nn.Parameter(self.app_line[i].data[..., t_l[mode0]:b_r[mode0], :])
-            mode0, mode1 = self.matMode[i]
-            self.density_plane[i] = torch.nn.Parameter(
-                self.density_plane[i].data[..., t_l[mode1]:b_r[mode1], t_l[mode0]:b_r[mode0]])
-            self.app_plane[i] = torch.nn.Parameter(
-                self.app_plane[i].data[..., t_l[mode1]:b_r[mode1], t_l[mode0]:b_r[mode0]])
+        lo = torch.round(torch.round((new_aabb[0] - self.aabb[0]) / self.units)).long()
+        hi = torch.minimum(torch.round((new_aabb[1] - self.aabb[0]) / self.units).long() + 1, self.gridSize)
+        for k, (m, v) in enumerate(zip(self.matMode, self.vecMode)):
+            for lines in (self.density_line, self.app_line):
+                self._rebind(lines, k, lines[k].data[..., lo[v]:hi[v], :])
+            for planes in (self.density_plane, self.app_plane):
+                self._rebind(planes, k, planes[k].data[..., lo[m[1]]:hi[m[1]], lo[m[0]]:hi[m[0]]])
         if not torch.all(self.alphaMask.gridSize == self.gridSize):
-            t_l_r, b_r_r = t_l / (self.gridSize - 1), (b_r - 1) / (self.gridSize - 1)
-            correct_aabb = torch.zeros_like(new_aabb)
-            correct_aabb[0] = (1 - t_l_r) * self.aabb[0] + t_l_r * self.aabb[1]
-            correct_aabb[1] = (1 - b_r_r) * self.aabb[0] + b_r_r * self.aabb[1]
-            print("aabb", new_aabb, "\ncorrect aabb", correct_aabb)
-            new_aabb = correct_aabb
-        newSize = b_r - t_l
+            f_lo, f_hi = lo / (self.gridSize - 1), (hi - 1) / (self.gridSize - 1)
+            snapped = torch.stack(((1 - f_lo) * self.aabb[0] + f_lo * self.aabb[1],
+                                   (1 - f_hi) * self.aabb[0] + f_hi * self.aabb[1]))
+            print("aabb", new_aabb, "\ncorrect aabb", snapped)
+            new_aabb = snapped
         self.aabb = new_aabb
-        self.update_stepSize((newSize[0], newSize[1], newSize[2]))
+        self.update_stepSize(tuple((hi - lo).tolist()))

@@ -244,6 +244,21 @@ def main():
     fx["relight_maps"] = (depth_c, normal_c, albedo_c, rough_c.repeat(1, 3), fresnel_c, acc_c)
     fx["relight_with_bg"], fx["relight_without_bg"] = acc_t * wo + (1.0 - acc_t) * bg, wo
     fx["relight_bg_lookup"] = env.get_light("sunny", rays[:, 3:]).clone()
+    # h) regularisers and grid maintenance (tensoRF_rotated_lights.py:60-92, :226-288) on a fresh copy
+    m2 = build_rotated(rot)
+    m2.load_state_dict(sd)
+    m2.alphaMask = rot.AlphaGridMask('cpu', fx["alpha_aabb"], fx["alpha_volume"])
+    from utils import TVLoss
+    tv = TVLoss()
+    fx["reg"] = dict(ortho=m2.vector_comp_diffs().detach().clone(), l1=m2.density_L1().detach().clone(),
+                     tv_density=m2.TV_loss_density(tv).detach().clone(), tv_app=m2.TV_loss_app(tv).detach().clone())
+    m2.shrink(new_aabb.clone())
+    fx["shrink"] = dict(aabb=m2.aabb.clone(), grid=m2.gridSize.tolist(), nSamples=m2.nSamples,
+                        density_plane0=m2.density_plane[0].detach().clone(), app_line2=m2.app_line[2].detach().clone())
+    m2.upsample_volume_grid([30, 31, 29])
+    fx["upsample"] = dict(grid=m2.gridSize.tolist(), nSamples=m2.nSamples, stepSize=float(m2.stepSize),
+                          density_plane1=m2.density_plane[1].detach().clone(),
+                          app_line0=m2.app_line[0].detach().clone())
     out["rotated"] = fx
     torch.save(fx, os.path.join(HERE, "rotated_g24.pt"))
 

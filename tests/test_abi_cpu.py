@@ -74,3 +74,34 @@ def test_light_model_matches_oracle(golden_rotated):
     from tensoir_b200.relight_utils import GGX_specular
     nrm, v2c, rough, fres = fx["ggx_in"]
     assert torch.equal(GGX_specular(nrm, v2c, fx["fixed_dirs"][None].repeat(9, 1, 1), rough, fres), fx["ggx"])
+
+
+def test_regularisers_and_grid_maintenance_match_reference(golden_rotated):
+    """vector_comp_diffs / density_L1 / TV losses, shrink and upsample_volume_grid (host-side, parameter-only) against
+    the reference's outputs; both maintenance ops rebind Parameters, which must invalidate the kernel-side shadows."""
+    from gpu_helpers import model_from_fixture
+    fx = golden_rotated
+    m = model_from_fixture(fx, "cpu")
+
+    def tv(x):     # utils.TVLoss (utils.py:143-162), restated
+        b, _, h, w = x.shape
+        ch, cw = x[:, :, 1:, :].numel() // b, x[:, :, :, 1:].numel() // b
+        return 2 * (torch.pow(x[:, :, 1:, :] - x[:, :, :h - 1, :], 2).sum() / ch
+                    + torch.pow(x[:, :, :, 1:] - x[:, :, :, :w - 1], 2).sum() / cw) / b
+    r = fx["reg"]
+    assert torch.allclose(m.vector_comp_diffs(), r["ortho"], rtol=1e-6)
+    assert torch.allclose(m.density_L1(), r["l1"], rtol=1e-6)
+    assert torch.allclose(m.TV_loss_density(tv), r["tv_density"], rtol=1e-6)
+    assert torch.allclose(m.TV_loss_app(tv), r["tv_app"], rtol=1e-6)
+    old = m.density_plane[0]
+    m.shrink(fx["new_aabb"].clone())
+    sh = fx["shrink"]
+    assert m.density_plane[0] is not old                                  # rebound, like the reference
+    assert torch.equal(m.aabb, sh["aabb"]) and m.gridSize.tolist() == sh["grid"] and m.nSamples == sh["nSamples"]
+    assert torch.equal(m.density_plane[0], sh["density_plane0"]) and torch.equal(m.app_line[2], sh["app_line2"])
+    assert m._host_geom["grid"] == sh["grid"]                             # host geometry cache follows
+    m.upsample_volume_grid([30, 31, 29])
+    up = fx["upsample"]
+    assert m.gridSize.tolist() == up["grid"] and m.nSamples == up["nSamples"]
+    assert abs(float(m.stepSize) - up["stepSize"]) < 1e-9
+    assert torch.equal(m.density_plane[1], up["density_plane1"]) and torch.equal(m.app_line[0], up["app_line0"])
