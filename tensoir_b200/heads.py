@@ -31,74 +31,106 @@ def _wgrad(g, a, splits=32):
     return out
 
 
-class _FusedHead(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, model, head, light, xn, x_in, li, w0, b0, w1, b1, w2, b2, basis, light_w, *app_params):
-        lib = _lib.load()
-        f = ops.device_field(model).refresh(model)
-        keep = []
-        mlp = mlp_struct(model, head, keep, light=light)
-        n = xn.shape[0]
-        dev = xn.device
-        act = 1 if head == "renderModule_normal" else 0
-        out = torch.empty(n, mlp.out_dim, device=dev)
-        need = any(ctx.needs_input_grad)     # grad mode is off inside Function.forward; this is the real signal
-        k0, in_dim, hid = 3 * f.aC, w0.shape[1], w0.shape[0]
-        xl = torch.empty(n, k0, device=dev) if need else None
-        inp = torch.empty(n, in_dim, device=dev) if need else None
-        h1 = torch.empty(n, hid, device=dev) if need else None
-        h2 = torch.empty(n, hid, device=dev) if need else None
-        nul = C.c_void_p(0)
-        _lib.check(lib.tir_app_mlp_points_save(
-            C.byref(f), C.byref(mlp), _lib.dptr(xn), _lib.dptr(x_in),
-            None if (li is None or light != "index") else _lib.dptr(li, torch.int32), n, act, _lib.dptr(out),
-            _lib.dptr(xl) if need else nul, _lib.dptr(inp) if need else nul, _lib.dptr(h1) if need else nul,
-            _lib.dptr(h2) if need else nul, _lib.stream_ptr()), "tir_app_mlp_points_save")
-        ctx.model, ctx.head, ctx.light, ctx.act = model, head, light, act
-        ctx.n_app_params = len(app_params)
-        ctx.save_for_backward(xn, li if li is not None else torch.empty(0, device=dev), out, xl, inp, h1, h2,
-                              w0, w1, w2, basis, light_w if light_w is not None else torch.empty(0, device=dev))
-        return out
+def _head_forward(model, head, light, xn, x_in, li, w0, need):
+    """One fused kernel launch; returns (out, xl, inp, h1, h2) (the dumps are None when no gradient is needed)."""
+    lib = _lib.load()
+    f = ops.device_field(model).refresh(model)
+    keep = []
+    mlp = mlp_struct(model, head, keep, light=light)
+    n, dev = xn.shape[0], xn.device
+    act = 1 if head == "renderModule_normal" else 0
+    out = torch.empty(n, mlp.out_dim, device=dev)
+    k0, in_dim, hid = 3 * f.aC, w0.shape[1], w0.shape[0]
+    xl = torch.empty(n, k0, device=dev) if need else None
+    inp = torch.empty(n, in_dim, device=dev) if need else None
+    h1 = torch.empty(n, hid, device=dev) if need else None
+    h2 = torch.empty(n, hid, device=dev) if need else None
+    nul = C.c_void_p(0)
+    _lib.check(lib.tir_app_mlp_points_save(
+        C.byref(f), C.byref(mlp), _lib.dptr(xn), _lib.dptr(x_in),
+        None if (li is None or li.numel() == 0 or light != "index") else _lib.dptr(li, torch.int32), n, act,
+        _lib.dptr(out), _lib.dptr(xl) if need else nul, _lib.dptr(inp) if need else nul,
+        _lib.dptr(h1) if need else nul, _lib.dptr(h2) if need else nul, _lib.stream_ptr()), "tir_app_mlp_points_save")
+    return out, xl, inp, h1, h2
+
+
+def _head_backward(act, light, g_out, out, xl, inp, h1, h2, w0, w1, w2, basis, light_w, li, x0):
+    """Hand-written backward of one head on its dumped activations.
+    -> (gw0, gb0, gw1, gb1, gw2, gb2, gbasis, glight or None, gx0 [n, 3*aC])."""
+    n = out.shape[0]
+    g_out = g_out.contiguous()
+    ones = torch.ones(n, device=out.device, dtype=out.dtype)
+
+    def colsum(t):                      # t.sum(0) as a cuBLAS gemv (the strided reduce kernel is 4x slower)
+        return torch.mv(t.t(), ones)
+    gz3 = g_out * (out * (1 - out) if act == 0 else 1 - out * out)
+    gw2, gb2 = _wgrad(gz3, h2), colsum(gz3)
+    gz2 = (gz3 @ w2) * (h2 > 0)
+    gw1, gb1 = _wgrad(gz2, h1), colsum(gz2)
+    gz1 = (gz2 @ w1) * (h1 > 0)
+    gw0, gb0 = _wgrad(gz1, inp), colsum(gz1)
+    gin = gz1 @ w0                                           # [n, in_dim]
+    F, pe = basis.shape[0], 2                                # fea_pe = 2 (checked by the kernel)
+    s0, c0 = F + 3, F + 3 + F * pe
+    freqs = 2.0 ** torch.arange(pe, device=out.device, dtype=inp.dtype)
+    gs, gc = gin[:, s0:s0 + F * pe].reshape(n, F, pe), gin[:, c0:c0 + F * pe].reshape(n, F, pe)
+    sn, cs = inp[:, s0:s0 + F * pe].reshape(n, F, pe), inp[:, c0:c0 + F * pe].reshape(n, F, pe)
+    gfeat = gin[:, :F] + ((gs * cs - gc * sn) * freqs).sum(-1)
+    gbasis = _wgrad(gfeat, xl)
+    gxl = gfeat @ basis                                       # [n, 3*aC]
+    if light == "none":
+        return gw0, gb0, gw1, gb1, gw2, gb2, gbasis, None, gxl
+    if light == "index":                                      # xl = x0 * light_line[li]
+        rows = light_w.index_select(0, li.long())
+        glight = torch.zeros_like(light_w).index_add_(0, li.long(), gxl * x0)
+    else:                                                     # xl = x0 * mean over lights
+        rows = light_w.mean(0, keepdim=True)
+        glight = ((gxl * x0).sum(0, keepdim=True) / light_w.shape[0]).expand_as(light_w)
+    return gw0, gb0, gw1, gb1, gw2, gb2, gbasis, glight, gxl * rows
+
+
+class _FusedHeads(torch.autograd.Function):
+    """Several heads evaluated at the SAME points: one kernel launch per head forward; in the backward the
+    appearance-product gradients of all heads are summed and scattered to the VM factors with ONE kernel."""
 
     @staticmethod
-    def backward(ctx, g_out):
-        xn, li, out, xl, inp, h1, h2, w0, w1, w2, basis, light_w = ctx.saved_tensors
-        model = ctx.model
-        n = xn.shape[0]
-        g_out = g_out.contiguous()
-        ones = torch.ones(n, device=xn.device, dtype=out.dtype)
+    def forward(ctx, model, specs, xn, basis, light_w, *rest):
+        nh = len(specs)
+        per = rest[:8 * nh]                  # per head: x_in, li, w0, b0, w1, b1, w2, b2
+        need = any(ctx.needs_input_grad)
+        outs, saved = [], []
+        for h, (head, light) in enumerate(specs):
+            x_in, li, w0, b0, w1, b1, w2, b2 = per[8 * h:8 * h + 8]
+            out, xl, inp, h1, h2 = _head_forward(model, head, light, xn, x_in, li, w0, need)
+            outs.append(out)
+            if need:
+                saved += [out, xl, inp, h1, h2, w0, w1, w2, li]
+        ctx.model, ctx.specs, ctx.need = model, specs, need
+        ctx.has_light = light_w is not None
+        ctx.save_for_backward(xn, basis, light_w if light_w is not None else torch.empty(0, device=xn.device), *saved)
+        return tuple(outs)
 
-        def colsum(t):                      # t.sum(0) as a cuBLAS gemv (the strided reduce kernel is 4x slower)
-            return torch.mv(t.t(), ones)
-        gz3 = g_out * (out * (1 - out) if ctx.act == 0 else 1 - out * out)
-        gw2, gb2 = _wgrad(gz3, h2), colsum(gz3)
-        gz2 = (gz3 @ w2) * (h2 > 0)
-        gw1, gb1 = _wgrad(gz2, h1), colsum(gz2)
-        gz1 = (gz2 @ w1) * (h1 > 0)
-        gw0, gb0 = _wgrad(gz1, inp), colsum(gz1)
-        gin = gz1 @ w0                                           # [n, in_dim]
-        F = basis.shape[0]
-        pe = (inp.shape[1] - F - 3 - 12) // (4 * F) * 2 if False else 2   # fea_pe = 2 (checked by the kernel)
-        s0, c0 = F + 3, F + 3 + F * pe
-        freqs = 2.0 ** torch.arange(pe, device=xn.device, dtype=inp.dtype)
-        gs, gc = gin[:, s0:s0 + F * pe].reshape(n, F, pe), gin[:, c0:c0 + F * pe].reshape(n, F, pe)
-        sn, cs = inp[:, s0:s0 + F * pe].reshape(n, F, pe), inp[:, c0:c0 + F * pe].reshape(n, F, pe)
-        gfeat = gin[:, :F] + ((gs * cs - gc * sn) * freqs).sum(-1)
-        gbasis = _wgrad(gfeat, xl)
-        gxl = gfeat @ basis                                       # [n, 3*aC]
-        # light factor: xl = x0 * lightvec
-        glight = None
-        if ctx.light == "none":
-            gx0 = gxl
-        else:
-            x0 = _raw_products(model, xn)
-            if ctx.light == "index":
-                rows = light_w.index_select(0, li.long())
-                glight = torch.zeros_like(light_w).index_add_(0, li.long(), gxl * x0)
-            else:  # mean over lights
-                rows = light_w.mean(0, keepdim=True)
-                glight = ((gxl * x0).sum(0, keepdim=True) / light_w.shape[0]).expand_as(light_w)
-            gx0 = gxl * rows
+    @staticmethod
+    def backward(ctx, *g_outs):
+        xn, basis, light_w, *saved = ctx.saved_tensors
+        model, specs = ctx.model, ctx.specs
+        n = xn.shape[0]
+        x0 = _raw_products(model, xn) if any(l != "none" for _, l in specs) else None
+        gbasis, glight, gx0 = None, None, None
+        per_grads = []
+        for h, (head, light) in enumerate(specs):
+            out, xl, inp, h1, h2, w0, w1, w2, li = saved[9 * h:9 * h + 9]
+            g = g_outs[h]
+            if g is None:
+                g = torch.zeros_like(out)
+            act = 1 if head == "renderModule_normal" else 0
+            gw0, gb0, gw1, gb1, gw2, gb2, gb_, gl_, gx_ = _head_backward(act, light, g, out, xl, inp, h1, h2, w0, w1,
+                                                                        w2, basis, light_w, li, x0)
+            per_grads += [None, None, gw0, gb0, gw1, gb1, gw2, gb2]
+            gbasis = gb_ if gbasis is None else gbasis + gb_
+            if gl_ is not None:
+                glight = gl_ if glight is None else glight + gl_
+            gx0 = gx_ if gx0 is None else gx0 + gx_
         lib = _lib.load()
         df = ops.device_field(model)
         f = df.refresh(model)
@@ -106,8 +138,7 @@ class _FusedHead(torch.autograd.Function):
         gx0 = gx0.contiguous()
         _lib.check(lib.tir_vm_app_products_bwd(C.byref(f), _lib.dptr(xn), n, _lib.dptr(gx0), _ptr_array(gp),
                                                _ptr_array(gl), _lib.stream_ptr()), "tir_vm_app_products_bwd")
-        return (None, None, None, None, None, None, gw0, gb0, gw1, gb1, gw2, gb2, gbasis, glight,
-                *_to_param_layout(gp, gl))
+        return (None, None, None, gbasis, glight if ctx.has_light else None, *per_grads, *_to_param_layout(gp, gl))
 
 
 def _raw_products(model, xn):
@@ -119,17 +150,30 @@ def _raw_products(model, xn):
     return out
 
 
-def fused_head(model, head: str, xn, x_in, light_idx=None, light: str = "index"):
-    """out = act(MLP_head([feat, x_in, PE(feat), PE(x_in)])), feat = basis_mat(plane*line(xn) * lightvec).
-    head: 'renderModule' (x_in = view dir, sigmoid) | 'renderModule_brdf' (x_in = position, sigmoid, 4 outputs) |
-    'renderModule_normal' (position, tanh).  light: 'index' | 'mean' | 'none'."""
-    mod = getattr(model, head)
+def fused_heads(model, xn, specs):
+    """Evaluate several heads at the same normalised points ``xn``.
+    specs: list of (head, x_in, light_idx or None, light) with head in {'renderModule' (x_in = view dir, sigmoid),
+    'renderModule_brdf' (x_in = position, sigmoid, 4 outputs), 'renderModule_normal' (position, tanh)} and
+    light in {'index', 'mean', 'none'}.  out_h = act(MLP_h([feat, x_in, PE(feat), PE(x_in)])) with
+    feat = basis_mat(plane*line(xn) * lightvec).  -> tuple of [n, out_dim_h]."""
     xn = xn.detach().reshape(-1, 3).float().contiguous()
-    x_in = x_in.detach().reshape(-1, 3).float().contiguous()
-    li = None if light_idx is None else light_idx.detach().reshape(-1).to(torch.int32).contiguous()
+    dev = xn.device
     ll = getattr(model, "light_line", None)
-    light_w = None if (ll is None or light == "none") else ll.weight
+    use_light = ll is not None and any(s[3] != "none" for s in specs)
+    light_w = ll.weight if use_light else None
+    flat, meta = [], []
+    for head, x_in, li, light in specs:
+        mod = getattr(model, head)
+        x_in = x_in.detach().reshape(-1, 3).float().contiguous()
+        li = (torch.empty(0, dtype=torch.int32, device=dev) if li is None
+              else li.detach().reshape(-1).to(torch.int32).contiguous())
+        flat += [x_in, li, mod.mlp[0].weight, mod.mlp[0].bias, mod.mlp[2].weight, mod.mlp[2].bias, mod.mlp[4].weight,
+                 mod.mlp[4].bias]
+        meta.append((head, light if ll is not None else "none"))
     params = list(model.app_plane) + list(model.app_line)
-    return _FusedHead.apply(model, head, light, xn, x_in, li, mod.mlp[0].weight, mod.mlp[0].bias, mod.mlp[2].weight,
-                            mod.mlp[2].bias, mod.mlp[4].weight, mod.mlp[4].bias, model.basis_mat.weight, light_w,
-                            *params)
+    return _FusedHeads.apply(model, tuple(meta), xn, model.basis_mat.weight, light_w, *flat, *params)
+
+
+def fused_head(model, head: str, xn, x_in, light_idx=None, light: str = "index"):
+    """Single-head convenience wrapper of :func:`fused_heads`."""
+    return fused_heads(model, xn, [(head, x_in, light_idx, light)])[0]

@@ -14,7 +14,7 @@ import torch.nn.functional as F
 from torch.profiler import record_function
 
 from . import vm_autograd as vm
-from .heads import fused_head
+from .heads import fused_head, fused_heads
 
 
 def _linear2srgb(t):
@@ -123,12 +123,17 @@ def _forward_relight_tail(model, rays, light_idx, white_bg, is_train, is_relight
       with record_function("tir::primary_app_stage"):
         vd = viewdirs.index_select(0, r_a)
         li = light_idx.reshape(-1).index_select(0, r_a)
-        # each head = ONE fused kernel launch (gather -> light factor -> basis -> PE -> MLP), see heads.py
-        rgb = fused_head(model, "renderModule", x_a, vd, li, light="index")
+        # each head = ONE fused kernel launch (gather -> light factor -> basis -> PE -> MLP); the heads evaluated at
+        # the same points share one backward scatter into the appearance factors (heads.py)
         if not is_relight:
+            rgb = fused_head(model, "renderModule", x_a, vd, li, light="index")
             rgb_map = _segment_sum(w_a[:, None] * rgb, r_a, n_rays)
         else:
-            brdf = fused_head(model, "renderModule_brdf", x_a, x_a, light="mean")
+            group = [("renderModule", vd, li, "index"), ("renderModule_brdf", x_a, None, "mean")]
+            if model.normals_kind != "purely_derived":
+                group.append(("renderModule_normal", x_a, None, "mean"))
+            res = fused_heads(model, x_a, group)
+            rgb, brdf = res[0], res[1]
             v_alb, v_rough = brdf[..., :3], (brdf[..., 3:4] * 0.9 + 0.09)
             # device-side draw, same shape/order as torch.randn_like(xyz_sampled[app_mask]) (tensorBase:937)
             draw = model.__dict__.get("_tir_randn_like")       # test hook: replay the oracle's CPU stream
@@ -138,14 +143,14 @@ def _forward_relight_tail(model, rays, light_idx, white_bg, is_train, is_relight
             r_cost = model.compute_relative_smoothness_loss(v_rough, brdf_j[..., 3:4] * 0.9 + 0.09)
             zero1 = torch.zeros_like(a_cost)
             if model.normals_kind == "purely_predicted":
-                v_n = fused_head(model, "renderModule_normal", x_a, x_a, light="mean")
+                v_n = res[2]
                 nd = no = zero1
             elif model.normals_kind == "purely_derived":
                 v_n = _derived_normals(model, x_a)
                 nd = no = zero1
             else:  # derived_plus_predicted
                 d_n = _derived_normals(model, x_a)
-                v_n = fused_head(model, "renderModule_normal", x_a, x_a, light="mean")
+                v_n = res[2]
                 nd = torch.sum(torch.pow(v_n - d_n, 2), dim=-1, keepdim=True)
                 no = torch.sum(vd * v_n, dim=-1, keepdim=True).clamp(min=0)
             # all 14 per-sample channels composited with ONE segment sum: [rgb 3 | normal 3 | albedo 3 | rough 1 |
