@@ -54,9 +54,6 @@ __device__ __forceinline__ LinearD linear_clamped(float gy, int D) {
   return l;
 }
 
-#define F4_OP(r, expr_x, expr_y, expr_z, expr_w) \
-  r.x = expr_x; r.y = expr_y; r.z = expr_z; r.w = expr_w;
-
 __device__ __forceinline__ float4 f4_comb4(float4 a, float4 b, float4 c, float4 d, float wa, float wb, float wc, float wd) {
   float4 r;
   r.x = a.x * wa + b.x * wb + c.x * wc + d.x * wd;

@@ -17,11 +17,6 @@ from . import vm_autograd as vm
 from .heads import fused_head, fused_heads
 
 
-def _linear2srgb(t):
-    from .relight_utils import linear2srgb_torch
-    return linear2srgb_torch(t)
-
-
 def _segment_sum(values, ray_id, n_rays):
     """sum over the samples of each ray: torch.sum(weight[..., None] * x, -2) of the reference."""
     if values.dim() == 1:
@@ -185,7 +180,8 @@ def _forward_relight_tail(model, rays, light_idx, white_bg, is_train, is_relight
         fresnel_map = fresnel_map + (1 - acc_map[..., None])
     rgb_map = rgb_map.clamp(0, 1)
     if rgb_map.shape[0] > 0:
-        rgb_map = _linear2srgb(rgb_map)
+        from .relight_utils import linear2srgb_torch
+        rgb_map = linear2srgb_torch(rgb_map)
     albedo_map = albedo_map.clamp(0, 1)
     fresnel_map = fresnel_map.clamp(0, 1)
     roughness_map = roughness_map.clamp(0, 1)

@@ -102,9 +102,8 @@ def render_with_BRDF(depth_map, normal_map, albedo_map, roughness_map, fresnel_m
         incident_light_dirs = st["dirs"]         # device buffer refilled by the host (same generator order)
     else:
         incident_light_dirs = tensoIR.gen_light_incident_dirs(method=sample_method).to(device)   # host draws, ref order
-    bs, nlights = surface_xyz.shape[0], incident_light_dirs.shape[0]
+    nlights = incident_light_dirs.shape[0]
     surf2c = safe_l2_normalize(-rays_d, dim=-1)
-    surf2l = cosine = None      # formed per (point, direction) inside the kernels
     # secondary rays: cosine test + 96-sample march + appearance MLP, generated on chip per (point, direction)
     with record_function("tir::secondary"):
         vis, indirect, _ = ops.secondary_radiance(
@@ -112,12 +111,12 @@ def render_with_BRDF(depth_map, normal_map, albedo_map, roughness_map, fresnel_m
             n_sample=args.second_nSample, near=args.second_near, far=args.second_far,
             counters=tensoIR.__dict__.get("_tir_counters"))
     with record_function("tir::shade_epilogue"):
-        return _shade(tensoIR, normal_map, albedo_map, roughness_map, fresnel_map, surf2c, surf2l, cosine, vis, indirect,
+        return _shade(tensoIR, normal_map, albedo_map, roughness_map, fresnel_map, surf2c, vis, indirect,
                       incident_light_dirs, light_idx, light_area_weight, nlights, sample_method, use_linear2srgb, device)
 
 
-def _shade(tensoIR, normal_map, albedo_map, roughness_map, fresnel_map, surf2c, surf2l, cosine, vis, indirect,
-           incident_light_dirs, light_idx, light_area_weight, nlights, sample_method, use_linear2srgb, device):
+def _shade(tensoIR, normal_map, albedo_map, roughness_map, fresnel_map, surf2c, vis, indirect, incident_light_dirs,
+           light_idx, light_area_weight, nlights, sample_method, use_linear2srgb, device):
     """Quadrature of the rendering equation, relight_utils.py:452-483: fused CUDA kernel (forward + analytic
     backward, csrc/tir_shade.cu); the SG light table stays in PyTorch (autograd reaches lgtSGs through it)."""
     from .shade import shade

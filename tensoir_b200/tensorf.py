@@ -9,7 +9,7 @@ from __future__ import annotations
 import torch
 import torch.nn.functional as F
 
-from . import ops, vm_autograd
+from . import vm_autograd
 from .tensorbase import TensorBase, AlphaGridMask, raw2alpha  # noqa: F401  (re-exported like the reference)
 
 
