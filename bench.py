@@ -249,7 +249,7 @@ def main():
         from tensoir_b200.static_step import StaticTrainStep
         graphed = StaticTrainStep(model, opt, a.batch, n_s, Args, lambda ret, m: loss_of(ret, target, m),
                                   grad_bucket=bucket, device=dev)
-        caps = graphed.calibrate(host_batches[:3])
+        caps = graphed.calibrate(host_batches[:8])     # max over 8 batches x 1.2 headroom; overflow is counted
         graphed.capture(warmup=3)
 
     def step(rays, li):

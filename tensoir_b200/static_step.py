@@ -38,7 +38,7 @@ class StaticTrainStep:
         self._pin_d = torch.zeros(model.envmap_h * model.envmap_w, 3).pin_memory()
 
     @torch.no_grad()
-    def calibrate(self, batches, headroom=1.3):
+    def calibrate(self, batches, headroom=1.2):
         """Size the static lists from eager marches over a few representative batches (max count x headroom)."""
         from . import primary
         self.model.__dict__.pop("_tir_static", None)
