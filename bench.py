@@ -134,6 +134,28 @@ def workload_config(a, parallelism):
                   f"({'exceed' if a.grid >= 256 else 'fit in'} L2 at this grid)"}
 
 
+def make_lego_state(grid, seed=20211202):
+    """CPU-side twin of tensoir_b200.synthetic.make_lego_model for the CPU baseline: the same field (same seed, same
+    init order, built with the host classes on the CPU - no kernels run) handed to the oracle as an OracleField, with
+    the alpha mask computed by the oracle itself.  Lives here (not in the package) because only bench.py / tests may
+    touch oracle/."""
+    from oracle import tensoir_oracle as O
+    from tensoir_b200.synthetic import install_lego_density
+    from tensoir_b200.tensorf import TensorVMSplit
+    torch.manual_seed(seed)
+    aabb = torch.tensor([[-1.5] * 3, [1.5] * 3])
+    m = TensorVMSplit(aabb, [grid] * 3, 'cpu', density_n_comp=[16] * 3, appearance_n_comp=[48] * 3, app_dim=27,
+                      near_far=[2.0, 6.0], shadingMode='MLP_Fea', alphaMask_thres=0.001, density_shift=-10,
+                      distance_scale=25, pos_pe=2, view_pe=2, fea_pe=2, featureC=128, step_ratio=0.5,
+                      fea2denseAct='softplus', normals_kind='derived_plus_predicted', light_rotation=["000"],
+                      light_kind='sg', numLgtSGs=128)
+    install_lego_density(m)
+    f = O.field_from_state_dict(m.state_dict(), aabb, [grid] * 3, kind="rotated", light_rotation=[0])
+    r = min(grid, 256)
+    O.update_alpha_mask(f, (r, r, r))
+    return f
+
+
 def _pick_threads(f, n_s):
     """torch CPU ops on the oracle's small tensors get SLOWER past some thread count (on the 128-core GPU host a step
     takes minutes at 128 threads); probe a few counts with one small secondary march each and keep the fastest -
@@ -163,7 +185,7 @@ def _pick_threads(f, n_s):
 def cpu_baseline(a, steps=2, warmup=1, budget_s=120.0):
     """Oracle (port of the reference) fwd+bwd+Adam on a bounded sample of the same workload, host cores only."""
     from oracle import tensoir_oracle as O
-    from tensoir_b200.synthetic import make_lego_state, hemisphere_poses, training_batch, n_samples_for
+    from tensoir_b200.synthetic import hemisphere_poses, training_batch, n_samples_for
     torch.set_num_threads(min(os.cpu_count() or 1, 32))
     f = make_lego_state(a.grid)
     n_s = n_samples_for(a.grid)

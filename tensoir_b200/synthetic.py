@@ -173,23 +173,3 @@ def make_lego_model(grid: int, device, *, lights=("000",), general=False, mask_r
 def n_samples_for(grid: int, step_ratio: float = 0.5, cap: int = 1000000) -> int:
     """min(args.nSamples, cal_n_samples(reso, step_ratio)) (train_tensoIR.py:161, utils.py:63-64)."""
     return min(cap, int(np.linalg.norm([grid] * 3) / step_ratio))
-
-
-def make_lego_state(grid: int, seed: int = SEED):
-    """CPU-side twin of make_lego_model for the oracle / CPU baseline: builds the same field (same seed, same init
-    order) with the tensoir_b200 host classes on the CPU — no kernels run for construction except the alpha mask,
-    which the oracle computes itself — and returns it as an oracle.OracleField."""
-    from oracle import tensoir_oracle as O          # bench/test-only path (cpu_baseline leg)
-    from .tensorf import TensorVMSplit
-    torch.manual_seed(seed)
-    aabb = torch.tensor([[-1.5] * 3, [1.5] * 3])
-    m = TensorVMSplit(aabb, [grid] * 3, 'cpu', density_n_comp=[16] * 3, appearance_n_comp=[48] * 3, app_dim=27,
-                      near_far=[2.0, 6.0], shadingMode='MLP_Fea', alphaMask_thres=0.001, density_shift=-10,
-                      distance_scale=25, pos_pe=2, view_pe=2, fea_pe=2, featureC=128, step_ratio=0.5,
-                      fea2denseAct='softplus', normals_kind='derived_plus_predicted', light_rotation=["000"],
-                      light_kind='sg', numLgtSGs=128)
-    install_lego_density(m)
-    f = O.field_from_state_dict(m.state_dict(), aabb, [grid] * 3, kind="rotated", light_rotation=[0])
-    r = min(grid, 256)
-    O.update_alpha_mask(f, (r, r, r))
-    return f

@@ -343,7 +343,7 @@ def test_cuda_graph_step(golden_rotated):
     assert all(l == l and l < 10 for l in losses), losses
     assert st.overflowed() == 0
     assert float((m.density_plane[0] - before).abs().max()) > 0
-    assert losses[-1] < losses[0] + 1e-3          # Adam on a fixed batch does not diverge
+    assert losses[-1] < losses[0] + 0.05          # Adam on a fixed batch does not diverge
     st.release()
 
 

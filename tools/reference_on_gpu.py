@@ -11,7 +11,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from oracle import tensoir_oracle as O   # noqa: E402
-from tensoir_b200.synthetic import make_lego_state, hemisphere_poses, training_batch, n_samples_for  # noqa: E402
+from bench import make_lego_state  # noqa: E402
+from tensoir_b200.synthetic import hemisphere_poses, training_batch, n_samples_for  # noqa: E402
 
 grid, batch, steps, warm = 300, 4096, 5, 2
 torch.set_num_threads(16)
