@@ -262,6 +262,24 @@ class TensorBase(torch.nn.Module):
                 phi, theta = torch.asin(a_b + a_j), th_b + th_j
             dirs = torch.stack([torch.cos(theta) * torch.cos(phi), torch.sin(theta) * torch.cos(phi),
                                 torch.sin(phi)], dim=-1)
+        elif method == 'importance_sample':
+            # tensorBase_rotated_lights.py:547-572: sample ``sample_number`` directions of a jittered 128x256 grid with
+            # probability ~ SG-light intensity * sin(theta); returns (dirs, rgbs, pdf) instead of a direction table
+            _, view_dirs = self.generate_envir_map_dir(128, 256, is_jittor=True)
+            envir_map = self.get_light_rgbs(view_dirs.reshape(-1, 3).to(device), device=device)[0]
+            with torch.no_grad():
+                envir_map = envir_map.reshape(128, 256, 3)
+                intensity = torch.sum(envir_map, dim=2, keepdim=True)
+                H, W, _ = intensity.shape
+                sin_theta = torch.sin(torch.linspace(0 + 0.5 / H, np.pi - 0.5 / H, H)).to(device)
+                pdf = intensity * sin_theta.view(-1, 1, 1)
+                pdf_to_sample = pdf / torch.sum(pdf)
+                pdf_to_compute = pdf_to_sample * H * W / (2 * np.pi * np.pi * sin_theta.view(-1, 1, 1))
+                idx = torch.multinomial(pdf_to_sample.view(-1), sample_number, replacement=True)
+                light_dir = view_dirs.view(-1, 3).to(device).index_select(0, idx)
+                light_rgb = envir_map.view(-1, 3).index_select(0, idx)
+                light_pdf = pdf_to_compute.view(-1, 1).index_select(0, idx)
+                return light_dir, light_rgb, light_pdf
         else:
             raise NotImplementedError(f"light sampling method {method!r}")
         return dirs.reshape(-1, 3)

@@ -244,6 +244,14 @@ def main():
     fx["relight_maps"] = (depth_c, normal_c, albedo_c, rough_c.repeat(1, 3), fresnel_c, acc_c)
     fx["relight_with_bg"], fx["relight_without_bg"] = acc_t * wo + (1.0 - acc_t) * bg, wo
     fx["relight_bg_lookup"] = env.get_light("sunny", rays[:, 3:]).clone()
+    # e2) importance sampling of the SG light (tensorBase_rotated_lights.py:547-572), seeded
+    _glr = m.get_light_rgbs          # the reference omits device= on this call (default 'cuda'); pin it to the CPU
+    m.get_light_rgbs = lambda dirs=None, device='cpu': _glr(dirs, device='cpu')
+    torch.manual_seed(41)
+    fx["importance_sample"] = tolist(m.gen_light_incident_dirs(sample_number=64, method='importance_sample',
+                                                               device='cpu'))
+    del m.get_light_rgbs
+
     # h) regularisers and grid maintenance (tensoRF_rotated_lights.py:60-92, :226-288) on a fresh copy
     m2 = build_rotated(rot)
     m2.load_state_dict(sd)

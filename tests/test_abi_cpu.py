@@ -105,3 +105,16 @@ def test_regularisers_and_grid_maintenance_match_reference(golden_rotated):
     assert m.gridSize.tolist() == up["grid"] and m.nSamples == up["nSamples"]
     assert abs(float(m.stepSize) - up["stepSize"]) < 1e-9
     assert torch.equal(m.density_plane[1], up["density_plane1"]) and torch.equal(m.app_line[0], up["app_line0"])
+
+
+def test_importance_sampled_light_dirs_match_reference(golden_rotated):
+    from gpu_helpers import model_from_fixture
+    fx = golden_rotated
+    m = model_from_fixture(fx, "cpu")
+    torch.manual_seed(41)
+    got = m.gen_light_incident_dirs(sample_number=64, method='importance_sample', device='cpu')
+    for g, w in zip(got, fx["importance_sample"]):
+        assert torch.equal(g.detach(), w)
+    torch.manual_seed(5)
+    a = m.gen_light_incident_dirs(method='stratifed_sample_equal_areas')
+    assert a.shape == (512, 3) and torch.allclose(a.norm(dim=-1), torch.ones(512), atol=1e-5)

@@ -464,3 +464,28 @@ def test_relight_chunk(golden_rotated):
     assert wv.shape == (64, 3) and torch.isfinite(wv).all() and float(wv.min()) >= 0 and float(wv.max()) <= 1
     miss = res["_primary"][5] <= 0.5
     assert torch.equal(wov[miss], torch.ones_like(wov[miss]))
+
+
+def test_config3_128_secondary_directions(golden_rotated):
+    """BASELINE config 3 variant: an 8x16 = 128-direction environment grid (constructor kwargs envmap_h / envmap_w,
+    tensorBase_rotated_lights.py:362-363) through the whole boundary, vs the oracle with the same grid."""
+    from tensoir_b200 import Renderer_TensoIR_train, TensorVMSplit, AlphaGridMask
+    fx = golden_rotated
+    m = TensorVMSplit(fx["aabb"].to(DEV), fx["grid_size"], DEV, density_n_comp=[16] * 3, appearance_n_comp=[48] * 3,
+                      app_dim=27, near_far=[2.0, 6.0], shadingMode='MLP_Fea', step_ratio=0.5, pos_pe=2, view_pe=2,
+                      fea_pe=2, featureC=128, normals_kind='derived_plus_predicted', light_rotation=['000', '120'],
+                      light_kind='sg', numLgtSGs=128, envmap_h=8, envmap_w=16)
+    m.load_state_dict({k: v.to(DEV) for k, v in fx["state_dict"].items()})
+    m.alphaMask = AlphaGridMask(DEV, fx["alpha_aabb"].to(DEV), fx["alpha_volume"].to(DEV))
+    f = oracle_field(fx)
+    f.envmap_h, f.envmap_w = 8, 16
+    m.__dict__["_tir_randn_like"] = lambda t: torch.randn(t.shape).to(t.device)
+    for method in ('fixed_envirmap', 'stratified_sampling'):
+        torch.manual_seed(13)
+        with torch.no_grad():
+            got = Renderer_TensoIR_train(fx["rays"], None, fx["light_idx"], m, N_samples=-1, is_train=False,
+                                         is_relight=True, sample_method=method, device=DEV, args=renderer_args(32))
+        torch.manual_seed(13)
+        want = O.renderer_train(f, fx["rays"], fx["light_idx"], -1, True, False, True, method, 160000, 32)
+        for k in ("rgb_with_brdf_map", "rgb_map", "normal_map", "acc_map"):
+            close(got[k], want[k], TOL, f"{method}:{k}")
