@@ -410,7 +410,6 @@ extern "C" int tir_app_mlp_points(const TirField* field, const TirMlp* mlp, cons
   int rc = check_shapes(field, mlp);
   if (rc) return rc;
   if (act != 0 && act != 1) return TIR_ERR_CONFIG;
-  if (n <= 0) return TIR_OK;
   MlpParams p{};
   p.f = *field; p.mlp = *mlp; p.pts_xn = xn; p.pts_x = x_in; p.n_points = n; p.light_idx = light_idx;
   p.out = out; p.act = act;

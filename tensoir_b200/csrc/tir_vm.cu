@@ -383,7 +383,6 @@ extern "C" int tir_vm_app_products(const TirField* field, const float* xn, int64
   if (n <= 0) return TIR_OK;   // empty input: nothing to do (pointers of empty tensors are NULL)
   if (!field || !xn || !out) return TIR_ERR_NULL;
   if (field->aC != 48) return TIR_ERR_SHAPE;
-  if (n <= 0) return TIR_OK;
   app_products_kernel<48><<<blocks_for(n * 3, 128), 128, 0, (cudaStream_t)stream>>>(*field, xn, n, out);
   return (int)cudaGetLastError();
 }
@@ -393,7 +392,6 @@ extern "C" int tir_vm_app_products_bwd(const TirField* field, const float* xn, i
   if (n <= 0) return TIR_OK;   // empty input: nothing to do (pointers of empty tensors are NULL)
   if (!field || !xn || !g_out || !g_plane || !g_line) return TIR_ERR_NULL;
   if (field->aC != 48) return TIR_ERR_SHAPE;
-  if (n <= 0) return TIR_OK;
   GradPtrs g;
   for (int k = 0; k < 3; ++k) { g.plane[k] = g_plane[k]; g.line[k] = g_line[k]; }
   app_products_bwd_kernel<48><<<blocks_for(n * 3, 128), 128, 0, (cudaStream_t)stream>>>(*field, xn, n, g_out, g);
@@ -405,7 +403,6 @@ extern "C" int tir_vm_density_bwd(const TirField* field, const float* xn, int64_
   if (n <= 0) return TIR_OK;   // empty input: nothing to do (pointers of empty tensors are NULL)
   if (!field || !xn || !g_feature || !g_plane || !g_line) return TIR_ERR_NULL;
   if (field->dC != 16) return TIR_ERR_SHAPE;
-  if (n <= 0) return TIR_OK;
   GradPtrs g;
   for (int k = 0; k < 3; ++k) { g.plane[k] = g_plane[k]; g.line[k] = g_line[k]; }
   density_bwd_kernel<16><<<blocks_for(n * 3, 128), 128, 0, (cudaStream_t)stream>>>(*field, xn, n, g_feature, g);
@@ -417,7 +414,6 @@ extern "C" int tir_vm_density_grad(const TirField* field, const float* xn, int64
   if (n <= 0) return TIR_OK;   // empty input: nothing to do (pointers of empty tensors are NULL)
   if (!field || !xn || !feature || !dfdx) return TIR_ERR_NULL;
   if (field->dC != 16) return TIR_ERR_SHAPE;
-  if (n <= 0) return TIR_OK;
   density_grad_kernel<16><<<blocks_for(n, 128), 128, 0, (cudaStream_t)stream>>>(*field, xn, n, feature, dfdx);
   return (int)cudaGetLastError();
 }
@@ -428,7 +424,6 @@ extern "C" int tir_vm_density_grad_bwd(const TirField* field, const float* xn, i
   if (n <= 0) return TIR_OK;   // empty input: nothing to do (pointers of empty tensors are NULL)
   if (!field || !xn || !g_plane || !g_line) return TIR_ERR_NULL;
   if (field->dC != 16) return TIR_ERR_SHAPE;
-  if (n <= 0) return TIR_OK;
   GradPtrs g;
   for (int k = 0; k < 3; ++k) { g.plane[k] = g_plane[k]; g.line[k] = g_line[k]; }
   density_grad_bwd_kernel<16><<<blocks_for(n * 3, 128), 128, 0, (cudaStream_t)stream>>>(*field, xn, n, g_feature,
