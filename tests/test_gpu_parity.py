@@ -24,6 +24,11 @@ def close(got, want, tol=TOL, what=""):
     assert bool((err <= bound).all()), (what, float(err.max()), float((err / bound).max()))
 
 
+def psnr(got, want):
+    mse = ((got.detach().float().cpu() - want.detach().float().cpu()) ** 2).mean()
+    return float(-10.0 * torch.log10(mse.clamp_min(1e-20)))
+
+
 @pytest.fixture(scope="module")
 def rot(golden_rotated):
     from tensoir_b200 import _lib
@@ -177,6 +182,9 @@ def test_boundary_eval(rot):
                                      chunk_size=160000, device=DEV, args=renderer_args(24))
     for k, w in fx["renderer_eval"].items():
         close(got[k], w, TOL, k)
+    # BASELINE metric, second half: PSNR of our images against the reference's (1e-4 parity => well above 70 dB)
+    for k in ("rgb_map", "rgb_with_brdf_map"):
+        assert psnr(got[k], fx["renderer_eval"][k]) > 70.0, k
     del m.__dict__["_tir_randn_like"]
 
 
