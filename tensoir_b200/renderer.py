@@ -67,4 +67,6 @@ def OctreeRender_trilinear_fast(rays, tensorf, chunk=4096, N_samples=-1, ndc_ray
                                      N_samples=N_samples)
         rgbs.append(rgb_map)
         depth_maps.append(depth_map)
+    if not rgbs:                      # zero rays: empty maps instead of torch.cat([]) raising
+        return (torch.zeros((0, 3), device=device), None, torch.zeros((0,), device=device), None, None)
     return torch.cat(rgbs), None, torch.cat(depth_maps), None, None

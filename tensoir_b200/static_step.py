@@ -100,6 +100,8 @@ class StaticTrainStep:
 
     def run(self, rays, light_idx):
         """One training step.  ``rays`` / ``light_idx`` may live on the host (pinned) or on the device."""
+        if self.graph is None:
+            raise RuntimeError("StaticTrainStep.run() before capture()")
         self.rays.copy_(rays, non_blocking=True)
         self.light_idx.copy_(light_idx.reshape(-1, 1), non_blocking=True)
         self._stage_host_randoms()
