@@ -2,9 +2,15 @@
 mask and the POD structs of include/tensoir_b200.h.
 
 PyTorch keeps owning the parameters in the reference NCHW layout (state_dict compatible); the
-kernels read shadows that are rebuilt whenever a parameter's (data_ptr, version, shape) changes —
-i.e. after every optimizer step and after shrink / upsample_volume_grid rebinding
-(tensoRF_rotated_lights.py:226-288).
+kernels read shadows that are rebuilt whenever the parameters may have changed:
+  * a parameter's (data_ptr, version, shape) differs — in-place edits, shrink / upsample_volume_grid rebinding
+    (tensoRF_rotated_lights.py:226-288, SURVEY.md §3.5), foreach / single-tensor optimizers;
+  * any torch optimizer has stepped since the last rebuild (global post-step hook).  Fused optimizers
+    (``Adam(fused=True)``, the one the CUDA-graph step uses) update parameters WITHOUT bumping the version
+    counter, so the version alone is not enough;
+  * the caller forces it (``refresh(model, force=True)``): every training forward does, so a captured CUDA graph
+    contains the repack at the start of each replay and never depends on host-side bookkeeping.
+Updates made outside torch.optim and without version bumps must be announced with :func:`mark_parameters_updated`.
 """
 from __future__ import annotations
 
@@ -18,6 +24,24 @@ from . import _lib
 
 def _key(ts):
     return tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in ts)
+
+
+# Bumped whenever parameters may have been updated behind the version counter's back (see module docstring).
+_param_epoch = 0
+
+
+def mark_parameters_updated(*_unused) -> None:
+    """Tell every DeviceField that parameters may have changed (next ``refresh`` rebuilds the shadows)."""
+    global _param_epoch
+    _param_epoch += 1
+
+
+def _install_optimizer_hook():
+    from torch.optim.optimizer import register_optimizer_step_post_hook
+    register_optimizer_step_post_hook(lambda opt, args, kwargs: mark_parameters_updated())
+
+
+_install_optimizer_hook()
 
 
 class DeviceField:
@@ -37,13 +61,13 @@ class DeviceField:
         _lib.check(lib.tir_pack_channels_last(_lib.dptr(src), _lib.dptr(out), Cc, H, W, _lib.stream_ptr()), "pack")
         return out
 
-    def refresh(self, model) -> "_lib.TirField":
+    def refresh(self, model, force: bool = False) -> "_lib.TirField":
         """Bring shadows + struct up to date with ``model`` (a TensorVMSplit-like module)."""
         lib = _lib.load()
         params = list(model.density_plane) + list(model.density_line) + list(model.app_plane) + list(model.app_line)
-        key = _key(params)
+        key = (_key(params), _param_epoch)
         s = self.struct
-        if key != self._vm_key:
+        if force or key != self._vm_key:
             self.dplane = [self._pack(lib, p) for p in model.density_plane]
             self.dline = [self._pack(lib, p) for p in model.density_line]
             self.aplane = [self._pack(lib, p) for p in model.app_plane]

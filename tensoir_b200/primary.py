@@ -13,6 +13,7 @@ import torch
 import torch.nn.functional as F
 from torch.profiler import record_function
 
+from . import ops
 from . import vm_autograd as vm
 from .heads import fused_head, fused_heads
 
@@ -49,6 +50,10 @@ def march(model, rays, is_train, n_samples, counters=None):
     """Shared front half: valid list -> sigma -> weights.  Returns a dict."""
     n_rays = rays.shape[0]
     st = model.__dict__.get("_tir_static")       # shape-static mode (CUDA-graph capture), see static_step.py
+    if is_train:
+        # a training forward always starts from freshly packed shadows: inside a captured graph this is what makes
+        # every replay read the parameters the previous replay's optimizer step wrote (device_field.py)
+        ops.device_field(model).refresh(model, force=True)
     jitter = None
     if is_train:
         if st is not None:

@@ -14,6 +14,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib
+from .device_field import mark_parameters_updated
 from .renderer import Renderer_TensoIR_train
 
 
@@ -106,6 +107,7 @@ class StaticTrainStep:
         self.light_idx.copy_(light_idx.reshape(-1, 1), non_blocking=True)
         self._stage_host_randoms()
         self.graph.replay()
+        mark_parameters_updated()        # the replayed optimizer step is invisible to the host-side bookkeeping
         _lib.launch_count += self.launches_per_replay
         return self.loss
 

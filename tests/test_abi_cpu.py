@@ -118,3 +118,42 @@ def test_importance_sampled_light_dirs_match_reference(golden_rotated):
     torch.manual_seed(5)
     a = m.gen_light_incident_dirs(method='stratifed_sample_equal_areas')
     assert a.shape == (512, 3) and torch.allclose(a.norm(dim=-1), torch.ones(512), atol=1e-5)
+
+
+def test_shadow_refresh_policy(golden_rotated, monkeypatch):
+    """DeviceField must rebuild the channel-last shadows after ANY parameter update: fused optimizers do not bump the
+    tensors' version counters, so the policy also listens to optimizer steps and honours force=True (decision logic
+    only: the pack kernel itself is replaced by a counting stub, no GPU needed)."""
+    from gpu_helpers import model_from_fixture
+    from tensoir_b200 import device_field
+    m = model_from_fixture(golden_rotated, "cpu")
+    m.alphaMask = None
+    packs = []
+
+    def fake_pack(self, lib, p):
+        packs.append(p.shape)
+        return p.detach()[0].permute(1, 2, 0).contiguous()
+    monkeypatch.setattr(device_field.DeviceField, "_pack", fake_pack)
+    df = device_field.DeviceField()
+    df.refresh(m)
+    assert len(packs) == 12
+    df.refresh(m)
+    assert len(packs) == 12                                  # nothing changed: no repack
+    for p in m.parameters():
+        p.grad = torch.zeros_like(p)
+    v0 = m.density_plane[0]._version
+    torch.optim.Adam(m.get_optparam_groups(0.02, 0.001), fused=True).step()
+    assert m.density_plane[0]._version == v0                 # the reason the version key alone is not enough
+    df.refresh(m)
+    assert len(packs) == 24                                  # optimizer step seen through the post-step hook
+    with torch.no_grad():
+        m.density_plane[0].mul_(1.0)                         # in-place edit: version bump
+    df.refresh(m)
+    assert len(packs) == 36
+    df.refresh(m, force=True)
+    assert len(packs) == 48
+    device_field.mark_parameters_updated()
+    df.refresh(m)
+    assert len(packs) == 60
+    df.refresh(m)
+    assert len(packs) == 60
