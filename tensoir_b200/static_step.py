@@ -97,12 +97,29 @@ class StaticTrainStep:
             self.loss = self._body()
         self.launches_per_replay = _lib.launch_count - l0
         torch.cuda.synchronize()
+        # The captured kernels hold raw pointers into buffers owned elsewhere (the sample-list scratch, the alpha-mask
+        # and VM shadows).  Keep references so that a later eager call that re-sizes / rebuilds them cannot hand the
+        # memory back to the allocator while this graph can still be replayed.
+        df = self.model.__dict__.get("_tir_device_field")
+        self._keepalive = [self.model.__dict__.get("_tir_scratch"), self.model.alphaMask,
+                           None if df is None else (df.dplane, df.dline, df.aplane, df.aline, df.amask, df.acell)]
+        self._captured_for = self._model_signature()
         return self
+
+    def _model_signature(self):
+        """Identity of everything the graph baked in by address: grid maintenance (updateAlphaMask / shrink /
+        upsample_volume_grid, train_tensoIR.py:386-422) replaces these objects and requires a new capture."""
+        m = self.model
+        vm = list(m.density_plane) + list(m.density_line) + list(m.app_plane) + list(m.app_line)
+        return (id(m.alphaMask), tuple((p.data_ptr(), tuple(p.shape)) for p in vm))
 
     def run(self, rays, light_idx):
         """One training step.  ``rays`` / ``light_idx`` may live on the host (pinned) or on the device."""
         if self.graph is None:
             raise RuntimeError("StaticTrainStep.run() before capture()")
+        if self._model_signature() != self._captured_for:
+            raise RuntimeError("the model's alpha mask or VM factors were replaced (updateAlphaMask / shrink / "
+                               "upsample_volume_grid) after capture(): build and capture a new StaticTrainStep")
         self.rays.copy_(rays, non_blocking=True)
         self.light_idx.copy_(light_idx.reshape(-1, 1), non_blocking=True)
         self._stage_host_randoms()

@@ -157,3 +157,26 @@ def test_shadow_refresh_policy(golden_rotated, monkeypatch):
     assert len(packs) == 60
     df.refresh(m)
     assert len(packs) == 60
+
+
+def test_static_step_recapture_guard(golden_rotated):
+    """The captured step bakes buffer addresses in; its signature must survive optimizer steps and change under the
+    grid-maintenance operations that replace parameters or the alpha mask (host logic only)."""
+    from gpu_helpers import model_from_fixture
+    from tensoir_b200 import AlphaGridMask
+    from tensoir_b200.static_step import StaticTrainStep
+    m = model_from_fixture(golden_rotated, "cpu")
+    st = StaticTrainStep.__new__(StaticTrainStep)
+    st.model = m
+    sig = st._model_signature()
+    for p in m.parameters():
+        p.grad = torch.zeros_like(p)
+    torch.optim.Adam(m.get_optparam_groups(0.02, 0.001), fused=True).step()
+    assert st._model_signature() == sig
+    old_mask = m.alphaMask
+    m.alphaMask = AlphaGridMask("cpu", old_mask.aabb, old_mask.alpha_volume.clone())
+    assert st._model_signature() != sig
+    m.alphaMask = old_mask
+    assert st._model_signature() == sig
+    m.upsample_volume_grid([g + 4 for g in golden_rotated["grid_size"]])
+    assert st._model_signature() != sig
