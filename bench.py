@@ -325,7 +325,6 @@ def main():
     if rank == 0:
         clocks.start()
     ms, cnt, launches = timed_region(dev_batches[a.warmup:], read_loss=False)
-    rays_total = a.batch * a.steps * world + (cnt["rays"] - a.batch * a.steps * world)   # primary + secondary
     rays_total = cnt["rays"]          # TIR_CNT_RAYS counts every marched ray: primary (valid-list pass) + secondary
     value = rays_total / (ms * 1e-3)
 
