@@ -9,6 +9,7 @@ Metric = (primary + secondary rays marched) / second, whole job.  `--impl refere
 algorithm (the oracle port under oracle/, the only part of this file that may execute oracle/) on the host cores.
 """
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -244,7 +245,8 @@ def main():
     from tensoir_b200.synthetic import make_lego_model, hemisphere_poses, training_batch, n_samples_for
     _lib.load()
 
-    model = make_lego_model(a.grid, dev)
+    with contextlib.redirect_stdout(sys.stderr):     # stdout carries exactly one line: the JSON result
+        model = make_lego_model(a.grid, dev)
     broadcast_parameters(model.parameters())
     params = []
     for grp in model.get_optparam_groups(0.02, 0.001):
@@ -428,7 +430,7 @@ def roofline(model, batch, n_s, dev, a):
                     "below the algorithmic bytes; frac is algorithmic bytes / time / measured HBM copy bandwidth",
             "ms_per_launch": ms_march, "algorithmic_bytes_per_launch": b_march,
             "units_per_launch": {"mask_queries": c["mask"], "density_samples": c["density"], "rays": c["rays"]},
-            "second_kernel": {"kernel": "app_mlp_kernel (appearance gather + basis + 150-128-128-3 MLP, fp32 SIMT)",
+            "second_kernel": {"kernel": "app_mlp_kernel (appearance gather + basis + 150-128-128-3 MLP, error-compensated BF16 mma.sync, fp32 accumulate)",
                               "ms_per_launch": ms_mlp, "app_samples": c["app"],
                               "achieved_GBps": b_mlp / (ms_mlp * 1e-3) / 1e9,
                               "achieved_TFLOPs": flops_mlp / (ms_mlp * 1e-3) / 1e12}}
