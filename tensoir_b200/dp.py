@@ -68,3 +68,29 @@ def broadcast_parameters(params: Iterable[torch.Tensor], src: int = 0, group=Non
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         for p in params:
             dist.broadcast(p.data, src=src, group=group)
+
+
+# ---- evaluation / relighting: views are independent, so they are sharded; the only exchange is the metric gather ----
+def shard_views(n_views: int, rank: int = None, world: int = None) -> List[int]:
+    """View ids rendered by ``rank`` (round-robin, so that ranks finish together when cost varies smoothly along a
+    camera path).  Defaults to the initialised process group, or a single process."""
+    if rank is None or world is None:
+        on = dist.is_available() and dist.is_initialized()
+        rank, world = (dist.get_rank(), dist.get_world_size()) if on else (0, 1)
+    return list(range(rank, n_views, world))
+
+
+def gather_view_results(local: dict, group=None) -> dict:
+    """Merge the per-view results {view_id: picklable metrics} of all ranks; every rank returns the full dict.
+    Small host objects only (PSNR / timing per view) — images stay on the rank that rendered them."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return dict(local)
+    parts = [None] * dist.get_world_size(group)
+    dist.all_gather_object(parts, dict(local), group=group)
+    merged = {}
+    for part in parts:
+        dup = merged.keys() & part.keys()
+        if dup:
+            raise RuntimeError(f"views rendered by more than one rank: {sorted(dup)}")
+        merged.update(part)
+    return merged

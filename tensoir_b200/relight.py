@@ -151,3 +151,28 @@ def relight_view(tensoIR, envir_light, light_names, frame_rays, light_rotation_i
     res = {n: (torch.cat(v[0]), torch.cat(v[1])) for n, v in out.items()}
     res["_primary"] = tuple(torch.cat([p[i] for p in prim]) for i in range(6))
     return res
+
+
+@torch.no_grad()
+def relight_views_sharded(tensoIR, envir_light, light_names, view_rays, *, gt=None, rank=None, world=None, **kw):
+    """The test-view loop of relight() (relight_importance.py:63-71) sharded over ranks (views are
+    independent; no data-path collective).  ``view_rays(i)`` returns the [H*W, 6] rays of view ``i`` (or pass a
+    sequence of ray tensors); ``gt`` optionally maps (view, light name) -> [H*W, 3] reference image for PSNR.
+    -> (local {view: relight_view result}, metrics of ALL views {view: {name: psnr or mean}} on every rank)."""
+    from .dp import gather_view_results, shard_views
+    n_views = len(view_rays) if hasattr(view_rays, "__len__") else kw.pop("n_views")
+    get = view_rays.__getitem__ if hasattr(view_rays, "__getitem__") else view_rays
+    local, metrics = {}, {}
+    for v in shard_views(n_views, rank, world):
+        res = relight_view(tensoIR, envir_light, light_names, get(v), **kw)
+        local[v] = res
+        m = {}
+        for n in light_names:
+            img = res[n][0]
+            if gt is not None:
+                mse = torch.mean((img - gt(v, n).to(img.device)) ** 2)
+                m[n] = float(-10.0 * torch.log10(mse.clamp_min(1e-20)))
+            else:
+                m[n] = float(img.mean())
+        metrics[v] = m
+    return local, gather_view_results(metrics)

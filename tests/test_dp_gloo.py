@@ -64,3 +64,29 @@ def test_shard_batch_partition():
         lo, hi = shard_batch(4096, r, 8)
         cover += list(range(lo, hi))
     assert cover == list(range(4096))
+
+
+def _view_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tensoir_b200 import relight
+    from tensoir_b200.dp import shard_views
+    mine = shard_views(7)
+    # the sharded relighting loop with the per-view renderer stubbed out (host logic only: sharding + metric gather)
+    relight.relight_view = lambda model, env, names, rays, **kw: {n: (rays[:, :3] * (1 + k), None)
+                                                                  for k, n in enumerate(names)}
+    views = [torch.full((4, 6), float(v)) for v in range(7)]
+    local, metrics = relight.relight_views_sharded(None, None, ["a", "b"], views)
+    out[rank] = (mine, sorted(local), metrics)
+    dist.destroy_process_group()
+
+
+def test_view_sharding_world2():
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_view_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    (m0, l0, met0), (m1, l1, met1) = out[0], out[1]
+    assert m0 == [0, 2, 4, 6] and m1 == [1, 3, 5] and l0 == m0 and l1 == m1     # disjoint, complete, round-robin
+    assert met0 == met1 and sorted(met0) == list(range(7))                         # every rank holds every metric
+    assert met0[3] == {"a": 3.0, "b": 6.0}
