@@ -18,6 +18,18 @@ from .device_field import mark_parameters_updated
 from .renderer import Renderer_TensoIR_train
 
 
+def lr_tensors(param_groups, device):
+    """Optimizer param groups with their learning rates turned into 0-dim fp32 tensors on ``device`` (what
+    ``torch.optim.Adam(..., capturable=True)`` reads on the device at every replay), so that learning-rate decay keeps
+    working under CUDA-graph replay (:meth:`StaticTrainStep.scale_lr`)."""
+    out = []
+    for grp in param_groups:
+        grp = dict(grp)
+        grp["lr"] = torch.as_tensor(float(grp["lr"]), dtype=torch.float32, device=device)
+        out.append(grp)
+    return out
+
+
 class StaticTrainStep:
     def __init__(self, model, optimizer, n_rays, n_samples, args, loss_fn, *, sample_method="stratified_sampling",
                  cap_valid=None, cap_app=None, grad_bucket=None, device=None):
@@ -127,6 +139,18 @@ class StaticTrainStep:
         mark_parameters_updated()        # the replayed optimizer step is invisible to the host-side bookkeeping
         _lib.launch_count += self.launches_per_replay
         return self.loss
+
+    def scale_lr(self, factor: float):
+        """The train loop's per-iteration decay ``param_group['lr'] = param_group['lr'] * lr_factor``
+        (train_tensoIR.py:380-381) for a captured step: a Python-float learning rate is baked into the graph at capture,
+        so the rates must be 0-dim device tensors (see :func:`lr_tensors`) and are scaled IN PLACE here, between
+        replays, where the next replay reads them."""
+        for grp in self.opt.param_groups:
+            lr = grp["lr"]
+            if not isinstance(lr, torch.Tensor):
+                raise TypeError("scale_lr() needs tensor learning rates: build the optimizer from "
+                                "static_step.lr_tensors(model.get_optparam_groups(...), device)")
+            lr.mul_(factor)
 
     def overflowed(self) -> int:
         """Number of steps whose lists exceeded the static capacities (host sync; call occasionally)."""

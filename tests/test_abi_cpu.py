@@ -180,3 +180,22 @@ def test_static_step_recapture_guard(golden_rotated):
     assert st._model_signature() == sig
     m.upsample_volume_grid([g + 4 for g in golden_rotated["grid_size"]])
     assert st._model_signature() != sig
+
+
+def test_lr_decay_under_captured_step_host_logic():
+    """lr_tensors / scale_lr: tensor learning rates scaled in place are what the next optimizer step uses."""
+    from tensoir_b200.static_step import StaticTrainStep, lr_tensors
+    p = torch.nn.Parameter(torch.zeros(4))
+    groups = lr_tensors([{"params": [p], "lr": 0.1}], "cpu")
+    opt = torch.optim.SGD(groups, lr=1.0, foreach=False)
+    st = StaticTrainStep.__new__(StaticTrainStep)
+    st.opt = opt
+    p.grad = torch.ones(4)
+    opt.step()
+    assert torch.allclose(p.detach(), torch.full((4,), -0.1))
+    st.scale_lr(0.5)
+    opt.step()
+    assert torch.allclose(p.detach(), torch.full((4,), -0.15))
+    st.opt = torch.optim.SGD([p], lr=0.1)
+    with pytest.raises(TypeError):
+        st.scale_lr(0.5)
