@@ -6,6 +6,12 @@ given a static capacity (rows past the real total are zero padding; overflow is 
 the host), host-drawn random numbers are written into static device buffers before each replay, and the whole
 forward + loss + backward + (optional gradient all-reduce) + Adam is captured once into a CUDA graph and replayed.
 
+Anything the host changes from step to step must live in device memory to reach a replay: ray batch / light indices
+(copied in by ``run``), the host-drawn randoms (staged by ``run``), learning rates (``lr_tensors`` + ``scale_lr``), and
+any loss weight that ``loss_fn`` varies over the iterations (the reference decays its TV weights,
+train_tensoIR.py:277-282) — keep those in 0-dim device tensors and update them in place between replays; Python floats
+are baked in at capture.  Grid maintenance (updateAlphaMask / shrink / upsample) needs a new capture (``run`` checks).
+
 Numerics are those of the eager path except for (i) the device-side xyz-noise draw, which has the padded shape and
 therefore a different random stream, and (ii) atomics ordering.  Parity tests run the eager path.
 """
