@@ -39,6 +39,9 @@ def parse():
     ap.add_argument("--cpu-rays", type=int, default=1024, help="bounded CPU-baseline sample (primary rays / step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="do not capture the step into a CUDA graph")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
+                    help="weak: every rank renders its own --batch rays (global batch = batch x N); strong: the --batch "
+                         "rays of a step are split over the ranks (SURVEY.md 8e: same draw on all ranks, contiguous slices)")
     return ap.parse_args()
 
 
@@ -114,7 +117,7 @@ def run_reference(a, rank, world):
         return
     out = cpu_baseline(a, steps=a.steps, warmup=a.warmup, budget_s=240.0)
     line = {"metric": METRIC, "value": out["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": out["steps_done"],
-            "warmup": a.warmup, "ms_per_step": out["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "warmup": a.warmup, "ms_per_step": out["ms_per_step"], "higher_is_better": True, "scaling": a.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
             "config": workload_config(a, parallelism=f"cpu{out['cores']}"),
             "cpu_baseline": {"value": out["value"], "unit": UNIT, "cores": out["cores"], "kind": "port",
@@ -129,7 +132,8 @@ def workload_config(a, parallelism):
     return {"workload": f"relight training step, lego-shaped synthetic scene (BASELINE configs[1] shape): "
                         f"TensorVMSplit {a.grid}^3 (16/48 comps, 3 MLP heads, SG light), batch {a.batch} rays of "
                         f"100 views 800x800, N_samples {n_samples_for(a.grid)}, 16x32 stratified secondary dirs x 96 "
-                        f"samples, fwd+bwd+Adam(fused)", "global_batch_rays": a.batch * max(1, a.gpus),
+                        f"samples, fwd+bwd+Adam(fused)",
+            "global_batch_rays": a.batch * (max(1, a.gpus) if getattr(a, "scaling", "weak") == "weak" else 1),
             "grid": a.grid, "parallelism": parallelism,
             "l2": "inputs change every step (new ray batch, updated parameters); VM tensors "
                   f"({'exceed' if a.grid >= 256 else 'fit in'} L2 at this grid)"}
@@ -260,10 +264,19 @@ def main():
     poses = hemisphere_poses(100)
     n_s = n_samples_for(a.grid)
     total = a.warmup + a.steps
-    # weak scaling: every rank draws its own 4096-ray batch each step (global batch = batch * world)
-    host_batches = [training_batch(poses, a.batch, it * world + rank) for it in range(2 * total)]
+    if a.scaling == "weak":
+        # every rank draws its own 4096-ray batch each step (global batch = batch * world)
+        per_rank = a.batch
+        host_batches = [training_batch(poses, a.batch, it * world + rank) for it in range(2 * total)]
+    else:
+        # the same global batch on every rank (same seed), rank r keeps its contiguous slice
+        from tensoir_b200.dp import shard_batch
+        lo, hi = shard_batch(a.batch, rank, world)
+        per_rank = hi - lo
+        host_batches = [tuple(t[lo:hi].contiguous() for t in training_batch(poses, a.batch, it))
+                        for it in range(2 * total)]
     pinned = [(r.pin_memory(), l.pin_memory()) for r, l in host_batches]
-    target = torch.full((a.batch, 3), 0.5, device=dev)
+    target = torch.full((per_rank, 3), 0.5, device=dev)
     counters = ops.new_counters(dev)
     model.__dict__["_tir_counters"] = counters
 
@@ -271,7 +284,7 @@ def main():
     if not a.eager:
         # whole-step CUDA graph: static-capacity sample lists, host randoms staged into device buffers, replay
         from tensoir_b200.static_step import StaticTrainStep
-        graphed = StaticTrainStep(model, opt, a.batch, n_s, Args, lambda ret, m: loss_of(ret, target, m),
+        graphed = StaticTrainStep(model, opt, per_rank, n_s, Args, lambda ret, m: loss_of(ret, target, m),
                                   grad_bucket=bucket, device=dev)
         caps = graphed.calibrate(host_batches[:8])     # max over 8 batches x 1.2 headroom; overflow is counted
         graphed.capture(warmup=3)
@@ -357,14 +370,14 @@ def main():
     # ---- roofline of the dominant kernel (the secondary march), timed live with CUDA events on the launch stream
     roof = roofline(model, dev_batches[-1], n_s, dev, a)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(a, f"dp{world}"),
-            "primary_rays_per_s": a.batch * a.steps * world / (ms * 1e-3),
-            "secondary_rays_per_s": (cnt["rays"] - a.batch * a.steps * world) / (ms * 1e-3),
+            "primary_rays_per_s": per_rank * a.steps * world / (ms * 1e-3),
+            "secondary_rays_per_s": (cnt["rays"] - per_rank * a.steps * world) / (ms * 1e-3),
             "counters_per_step": {k: v / a.steps for k, v in cnt.items()},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
                     # rays + light_idx + the host-drawn per-ray jitter and stratified light directions
-                    "h2d_bytes_per_step": (a.batch * (6 * 4 + 4) + a.batch * 4 + 512 * 3 * 4) * world,
+                    "h2d_bytes_per_step": (per_rank * (6 * 4 + 4) + per_rank * 4 + 512 * 3 * 4) * world,
                     "d2h_bytes_per_step": 4 * world},
             "gpu_launches": launches, "clocks": clk, "roofline": roof,
             "execution": ("eager" if a.eager else f"cuda-graph replay of the whole step (static list capacities "
