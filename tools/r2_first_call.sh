@@ -1,6 +1,6 @@
 #!/bin/bash
 # First GPU call of round 2: everything round 1 prepared without being able to run it, in ONE gpurun invocation.
-#   /usr/local/graft/bin/gpurun --timeout 3000 -- 'bash tools/r2_first_call.sh'
+#   /usr/local/graft/bin/gpurun --timeout 3600 -- 'bash tools/r2_first_call.sh'
 # Results land in gpurun_out/r2_first/.  Every step has its own timeout and never aborts the following ones.
 set -u
 OUT=gpurun_out/r2_first
@@ -42,14 +42,15 @@ tail -3 "$OUT/cl_pytest_gpu.log" | tee -a "$OUT/summary.txt"
 ( cd "$CL" && timeout 500 python bench.py --no-cpu-baseline ) > "$OUT/bench_channels_last.json" 2> "$OUT/bench_channels_last.err"
 echo "bench rc=$?" | tee -a "$OUT/summary.txt"
 
-step "6b. product patches: tail = fused primary tail/epilogue; both = + channel-last parameters; all = + batched heads backward"
-for variant in tail both all; do
+step "6b. product patches: term = exact early termination in the march; tail = fused primary tail/epilogue; both = tail + channel-last parameters; all = everything incl. batched heads backward"
+for variant in term tail both all; do
   D=/tmp/tir_$variant
   rm -rf "$D"; mkdir -p "$D"
   tar --exclude=./gpurun_out --exclude=./.git -cf - . | tar -xf - -C "$D"
-  ( cd "$D" && { [ $variant != tail ] && git apply experiments/channels_last_params/product.patch; true; } \
-      && git apply experiments/primary_tail/product.patch \
+  ( cd "$D" && { [ $variant = both -o $variant = all ] && git apply experiments/channels_last_params/product.patch; true; } \
+      && { [ $variant != term ] && git apply experiments/primary_tail/product.patch; true; } \
       && { [ $variant = all ] && git apply experiments/batched_heads/product.patch; true; } \
+      && { [ $variant = all -o $variant = term ] && git apply experiments/exact_termination/product.patch; true; } \
       && python -c "import __graft_entry__ as g; g.build(force=True)" ) > "$OUT/${variant}_apply_build.log" 2>&1
   echo "$variant apply+build rc=$?" | tee -a "$OUT/summary.txt"
   ( cd "$D" && timeout 700 python -m pytest tests -q -m gpu -x ) > "$OUT/${variant}_pytest_gpu.log" 2>&1
