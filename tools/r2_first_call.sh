@@ -32,32 +32,27 @@ timeout 300 python experiments/primary_tail/check_gpu.py > "$OUT/tail_gpu.txt" 2
 timeout 300 python experiments/primary_epilogue/check_gpu.py > "$OUT/epilogue_gpu.txt" 2>&1; echo "rc=$?" | tee -a "$OUT/summary.txt"
 cat "$OUT/tail_gpu.txt" "$OUT/epilogue_gpu.txt" | tee -a "$OUT/summary.txt"
 
-step "6. channel-last VM parameters (experiments/channels_last_params/product.patch) in a scratch copy"
-CL=/tmp/tir_channels_last
-rm -rf "$CL"; mkdir -p "$CL"
-tar --exclude=./gpurun_out --exclude=./.git -cf - . | tar -xf - -C "$CL"
-( cd "$CL" && git apply experiments/channels_last_params/product.patch ) > "$OUT/cl_apply.log" 2>&1; echo "apply rc=$?" | tee -a "$OUT/summary.txt"
-( cd "$CL" && timeout 700 python -m pytest tests -q -m gpu -x ) > "$OUT/cl_pytest_gpu.log" 2>&1; echo "pytest rc=$?" | tee -a "$OUT/summary.txt"
-tail -3 "$OUT/cl_pytest_gpu.log" | tee -a "$OUT/summary.txt"
-( cd "$CL" && timeout 500 python bench.py --no-cpu-baseline ) > "$OUT/bench_channels_last.json" 2> "$OUT/bench_channels_last.err"
-echo "bench rc=$?" | tee -a "$OUT/summary.txt"
-
-step "6b. product patches: term = exact early termination in the march; tail = fused primary tail/epilogue; both = tail + channel-last parameters; all = everything incl. batched heads backward"
-for variant in term tail both all; do
-  D=/tmp/tir_$variant
-  rm -rf "$D"; mkdir -p "$D"
-  tar --exclude=./gpurun_out --exclude=./.git -cf - . | tar -xf - -C "$D"
-  ( cd "$D" && { [ $variant = both -o $variant = all ] && git apply experiments/channels_last_params/product.patch; true; } \
-      && { [ $variant != term ] && git apply experiments/primary_tail/product.patch; true; } \
-      && { [ $variant = all ] && git apply experiments/batched_heads/product.patch; true; } \
-      && { [ $variant = all -o $variant = term ] && git apply experiments/exact_termination/product.patch; true; } \
-      && python -c "import __graft_entry__ as g; g.build(force=True)" ) > "$OUT/${variant}_apply_build.log" 2>&1
-  echo "$variant apply+build rc=$?" | tee -a "$OUT/summary.txt"
-  ( cd "$D" && timeout 700 python -m pytest tests -q -m gpu -x ) > "$OUT/${variant}_pytest_gpu.log" 2>&1
-  echo "$variant pytest rc=$?" | tee -a "$OUT/summary.txt"
-  tail -3 "$OUT/${variant}_pytest_gpu.log" | tee -a "$OUT/summary.txt"
-  ( cd "$D" && timeout 500 python bench.py --no-cpu-baseline ) > "$OUT/bench_$variant.json" 2> "$OUT/bench_$variant.err"
-  echo "$variant bench rc=$?" | tee -a "$OUT/summary.txt"
+step "6. staged product patches (experiments/stack/): cumulative prefixes 1 exact termination, 2 + lean march, 3 + channel-last parameters, 4 + fused tail/epilogue, 5 + batched heads backward"
+D=/tmp/tir_stack
+rm -rf "$D"; mkdir -p "$D"
+tar --exclude=./gpurun_out --exclude=./.git -cf - . | tar -xf - -C "$D"
+for patch in experiments/stack/*.patch; do
+  tag=$(basename "$patch" .patch)
+  ( cd "$D" && git apply "$patch" && python -c "import __graft_entry__ as g; g.build(force=True)" ) > "$OUT/${tag}_apply_build.log" 2>&1
+  echo "$tag apply+build rc=$?" | tee -a "$OUT/summary.txt"
+  ( cd "$D" && timeout 700 python -m pytest tests -q -m gpu -x ) > "$OUT/${tag}_pytest_gpu.log" 2>&1
+  echo "$tag pytest rc=$?" | tee -a "$OUT/summary.txt"
+  tail -3 "$OUT/${tag}_pytest_gpu.log" | tee -a "$OUT/summary.txt"
+  ( cd "$D" && timeout 500 python bench.py --no-cpu-baseline ) > "$OUT/bench_${tag}.json" 2> "$OUT/bench_${tag}.err"
+  echo "$tag bench rc=$?" | tee -a "$OUT/summary.txt"
+  python - "$OUT/bench_${tag}.json" <<'PY' | tee -a "$OUT/summary.txt"
+import json, sys
+try:
+    d = [json.loads(l) for l in open(sys.argv[1]) if l.startswith("{")][-1]
+    print(f"   {d['ms_per_step']:.3f} ms/step, {d['value'] / 1e6:.1f} M rays/s, launches {d['gpu_launches']}, march {d['roofline']['ms_per_launch']:.3f} ms")
+except Exception as e:
+    print("   no bench line:", e)
+PY
 done
 
 step "7. PSNR of a 96x96 crop against the reference algorithm on the same GPU"
