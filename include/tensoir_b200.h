@@ -105,7 +105,13 @@ typedef struct TirMarchCfg {
                               point, tensorBase:803-804) */
 } TirMarchCfg;
 
-enum { TIR_MARCH_NO_BBOX = 1 };
+enum {
+  TIR_MARCH_NO_BBOX = 1,
+  /* Production mode of the marches: work whose only effect would be on TIR_CNT_MASK / TIR_CNT_DENSITY is skipped (the
+   * rest of a ray whose transmittance has underflowed to exactly 0), so those two slots count the queries actually made
+   * instead of the queries the reference makes.  All outputs, the appearance list and the other counters are unchanged. */
+  TIR_MARCH_LEAN_COUNTERS = 2
+};
 
 /* One compacted appearance sample produced by the march (w > weight_thres), consumed by tir_app_mlp. */
 typedef struct TirAppSample {
@@ -252,6 +258,46 @@ int tir_composite_bwd(const float* sigma, const float* dist, const int64_t* offs
                       float distance_scale, const float* weight, const float* trans, const float* g_weight,
                       float* g_sigma, int64_t limit, const float* z, const float* g_acc /* [n_rays] or NULL */,
                       const float* g_depth /* [n_rays] or NULL */, void* stream);
+
+/* ---- fused end of the primary march (tensorBase_rotated_lights.py:930-1036) --------------------------------- */
+
+/* Per appearance sample: BRDF split, relative-smoothness costs (:858-863), normals_diff / orientation terms (:952-961),
+ * weighting and the per-ray sums torch.sum(weight[..., None] * x, -2) (:974-975) of 14 channels
+ *   [rgb 3 | normal 3 | albedo 3 | roughness | albedo cost | roughness cost | normals_diff | orientation].
+ * w [n], ray [n] int64 (ray of each sample), rgb / vn [n,3], brdf / brdfj [n,4] (BRDF head at x and at x + noise),
+ * dn [n,3] derived normals or NULL (then the last two channels are 0), viewdirs [n_rays,3]
+ * -> packed [n_rays,14], accumulated with atomics (caller zeroes). */
+int tir_tail_fwd(int64_t n, const float* w, const int64_t* ray, const float* rgb, const float* brdf,
+                 const float* brdfj, const float* vn, const float* dn, const float* viewdirs, float* packed,
+                 void* stream);
+/* analytic backward: g_packed [n_rays,14] -> per-sample gradients (g_dn may be NULL when dn is). */
+int tir_tail_bwd(int64_t n, const float* w, const int64_t* ray, const float* rgb, const float* brdf,
+                 const float* brdfj, const float* vn, const float* dn, const float* viewdirs, const float* g_packed,
+                 float* g_w, float* g_rgb, float* g_brdf, float* g_brdfj, float* g_vn, float* g_dn, void* stream);
+
+/* per-ray maps of the 12-tuple (or their gradients) */
+typedef struct TirRayMaps {
+  float* rgb;      /* [n,3] sRGB */
+  float* depth;    /* [n]   */
+  float* normal;   /* [n,3] unit */
+  float* albedo;   /* [n,3] */
+  float* rough;    /* [n]   */
+  float* fresnel;  /* [n,3] */
+  float* nd;       /* [n] normals_diff_map */
+  float* no;       /* [n] normals_orientation_loss_map */
+} TirRayMaps;
+
+/* Per ray: background compositing with (1 - acc) when bg != 0 (:1004-1012), clamps, linear2srgb_torch
+ * (relight_utils.py:489-515), safe_l2_normalize of the normal map, acc_mask = acc > 0.5, and the two scalar
+ * smoothness losses mean(albedo cost), mean(roughness cost) accumulated into losses[2] (caller zeroes).
+ * packed [n,14] from tir_tail_fwd, acc / depth [n] from tir_composite_fwd, rays [n,6]. */
+int tir_epilogue_fwd(int64_t n, const float* packed, const float* acc, const float* depth, const float* rays,
+                     float fresnel0, int32_t bg, const TirRayMaps* out, uint8_t* acc_mask, float* losses,
+                     void* stream);
+/* analytic backward; every pointer in g_out and the two scalar-loss gradients may be NULL. */
+int tir_epilogue_bwd(int64_t n, const float* packed, const float* acc, const float* depth, const float* rays,
+                     float fresnel0, int32_t bg, const TirRayMaps* g_out, const float* g_loss_albedo,
+                     const float* g_loss_rough, float* g_packed, float* g_acc, float* g_depth, void* stream);
 
 #ifdef __cplusplus
 }

@@ -50,6 +50,11 @@ class TirMarchCfg(C.Structure):
 
 
 MARCH_NO_BBOX = 1
+MARCH_LEAN_COUNTERS = 2
+
+
+class TirRayMaps(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("rgb", "depth", "normal", "albedo", "rough", "fresnel", "nd", "no")]
 
 
 APP_SAMPLE_BYTES = 24  # sizeof(TirAppSample)
@@ -98,6 +103,13 @@ EXPORTS = {
                                     f32p, f32p, f32p, C.c_void_p]),
     "tir_composite_bwd": (C.c_int, [f32p, f32p, C.c_void_p, C.c_int64, C.c_float, f32p, f32p, f32p, f32p,
                                     C.c_int64, f32p, f32p, f32p, C.c_void_p]),
+    "tir_tail_fwd": (C.c_int, [C.c_int64, f32p, C.c_void_p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, C.c_void_p]),
+    "tir_tail_bwd": (C.c_int, [C.c_int64, f32p, C.c_void_p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p,
+                               f32p, f32p, f32p, C.c_void_p]),
+    "tir_epilogue_fwd": (C.c_int, [C.c_int64, f32p, f32p, f32p, f32p, C.c_float, C.c_int32, C.POINTER(TirRayMaps),
+                                   C.c_void_p, f32p, C.c_void_p]),
+    "tir_epilogue_bwd": (C.c_int, [C.c_int64, f32p, f32p, f32p, f32p, C.c_float, C.c_int32, C.POINTER(TirRayMaps),
+                                   f32p, f32p, f32p, f32p, f32p, C.c_void_p]),
 }
 
 # kernels launched per entry point (for bench.py's gpu_launches claim)
@@ -107,7 +119,8 @@ KERNELS_PER_CALL = {"tir_pack_channels_last": 1, "tir_unpack_channels_last_add":
                     "tir_shade_fwd": 1, "tir_shade_bwd": 1, "tir_app_mlp_points": 1, "tir_app_mlp_points_save": 1, "tir_vm_app_products": 1, "tir_vm_app_products_bwd": 1,
                     "tir_vm_density_bwd": 1, "tir_vm_density_grad": 1, "tir_vm_density_grad_bwd": 1,
                     "tir_valid_samples_count": 1, "tir_valid_samples_fill": 1, "tir_composite_fwd": 1,
-                    "tir_composite_bwd": 1}
+                    "tir_composite_bwd": 1, "tir_tail_fwd": 1, "tir_tail_bwd": 1, "tir_epilogue_fwd": 1,
+                    "tir_epilogue_bwd": 1}
 launch_count = 0
 
 _lib = None

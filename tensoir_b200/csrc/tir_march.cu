@@ -191,7 +191,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, kBlocksPerSM) march_kerne
     };
 
     int pushed = 0;
+    const bool lean = (p.cfg.flags & TIR_MARCH_LEAN_COUNTERS) != 0;
     for (int base = 0; base < N; base += 32) {
+      // lean mode: a ray whose carried transmittance is exactly 0 cannot change any output any more (see below), and
+      // nobody asked for the mask / density counts of its remaining samples, so the rest of the ray is skipped
+      if (lean && c_ray == ray && c_T == 0.f) break;
       const int s = base + lane;
       bool valid = false;
       float nx = 0.f, ny = 0.f, nz = 0.f, z = 0.f;
@@ -212,6 +216,15 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, kBlocksPerSM) march_kerne
           ny = __fsub_rn(__fmul_rn(__fsub_rn(py, f.aabb_lo[1]), f.inv_aabb[1]), 1.f);
           nz = __fsub_rn(__fmul_rn(__fsub_rn(pz, f.aabb_lo[2]), f.inv_aabb[2]), 1.f);
         }
+      }
+      // Exact early termination: once the transmittance carried for THIS ray has underflowed to exactly 0.0f, every
+      // later weight is alpha * 0 = 0 and T stays 0 (0 * finite), so the remaining samples cannot change t_last, acc,
+      // depth or the appearance list.  Their gather is skipped; they are still counted, so the counters keep meaning
+      // "samples the reference evaluates".  (c_ray, c_T are warp-uniform; samples of the ray that are still queued
+      // simply keep the state unknown, which is conservative.)
+      if (c_ray == ray && c_T == 0.f) {
+        c_density += valid;
+        valid = false;
       }
       const unsigned m = __ballot_sync(0xffffffffu, valid);
       if (valid) {

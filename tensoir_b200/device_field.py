@@ -56,6 +56,8 @@ class DeviceField:
     # ---- VM factors -------------------------------------------------------------------
     def _pack(self, lib, p):
         _, Cc, H, W = p.shape
+        if Cc > 1 and p.is_contiguous(memory_format=torch.channels_last):
+            return p.detach()[0].permute(1, 2, 0)       # [H,W,C] view of the parameter's own storage: nothing to copy
         src = p.detach().contiguous()
         out = torch.empty((H, W, Cc), device=p.device, dtype=torch.float32)
         _lib.check(lib.tir_pack_channels_last(_lib.dptr(src), _lib.dptr(out), Cc, H, W, _lib.stream_ptr()), "pack")

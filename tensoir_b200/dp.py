@@ -32,7 +32,11 @@ class GradBucket:
         o = 0
         self.views = []
         for p in self.params:
-            v = self.flat[o:o + p.numel()].view_as(p)
+            # same strides as the parameter (channel-last VM factors): fused optimizers require params and grads to
+            # share one layout, and autograd's layout contract then never re-lays the gradient out
+            chunk = self.flat[o:o + p.numel()]
+            dense = p.is_contiguous() or (p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last))
+            v = chunk.as_strided(p.shape, p.stride()) if dense else chunk.view_as(p)
             self.views.append(v)
             o += p.numel()
 
@@ -67,7 +71,10 @@ def shard_batch(n: int, rank: int, world: int):
 def broadcast_parameters(params: Iterable[torch.Tensor], src: int = 0, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         for p in params:
-            dist.broadcast(p.data, src=src, group=group)
+            t = p.data
+            if not t.is_contiguous() and t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last):
+                t = t.permute(0, 2, 3, 1)               # the same storage seen as a contiguous tensor (NCCL needs one)
+            dist.broadcast(t, src=src, group=group)
 
 
 # ---- evaluation / relighting: views are independent, so they are sharded; the only exchange is the metric gather ----

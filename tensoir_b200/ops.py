@@ -102,6 +102,8 @@ def march_density(model, rays_o, rays_d, *, table=None, n_samples=-1, jitter=Non
     keep = []
     cfg = march_cfg(model, table=table, n_samples=n_samples, jitter=jitter, keep=keep)
     ro, rd = _f32c(rays_o.reshape(-1, 3)), _f32c(rays_d.reshape(-1, 3))
+    if lean_counters(model):
+        cfg.flags |= _lib.MARCH_LEAN_COUNTERS
     n = ro.shape[0]
     t_last = torch.ones(n, device=ro.device)
     acc = torch.zeros(n, device=ro.device)
@@ -146,6 +148,8 @@ def march_radiance(model, rays_o, rays_d, light_idx=None, *, table=None, n_sampl
     f = device_field(model).refresh(model)
     keep = []
     cfg = march_cfg(model, table=table, n_samples=n_samples, jitter=jitter, keep=keep)
+    if lean_counters(model):
+        cfg.flags |= _lib.MARCH_LEAN_COUNTERS
     mlp = mlp_struct(model, head, keep, light="index" if light_idx is not None else "none")
     ro, rd = _f32c(rays_o.reshape(-1, 3)), _f32c(rays_d.reshape(-1, 3))
     li = _i32c(light_idx)
@@ -166,6 +170,12 @@ def march_radiance(model, rays_o, rays_d, light_idx=None, *, table=None, n_sampl
     return t_last, acc, depth, rgb, sc
 
 
+def lean_counters(model) -> bool:
+    """True when the model runs its marches in production mode (``model.__dict__['_tir_lean']``): the mask / density
+    counters then count the queries actually made (include/tensoir_b200.h: TIR_MARCH_LEAN_COUNTERS)."""
+    return bool(model.__dict__.get("_tir_lean", False))
+
+
 def secondary_radiance(model, surf_xyz, normals, light_idx, dirs, *, n_sample=96, near=0.05, far=1.5,
                        counters=None, capacity=None):
     """Secondary shading of render_with_BRDF -> (vis [n_pts,n_dirs,1], indirect [n_pts,n_dirs,3], scratch)."""
@@ -174,6 +184,8 @@ def secondary_radiance(model, surf_xyz, normals, light_idx, dirs, *, n_sample=96
     keep = []
     dev = surf_xyz.device
     cfg = march_cfg(model, table=equal_z_table(n_sample, near, far, dev), keep=keep)
+    if lean_counters(model):
+        cfg.flags |= _lib.MARCH_LEAN_COUNTERS
     mlp = mlp_struct(model, "renderModule", keep, light="index")
     sx, nr, dr = _f32c(surf_xyz.reshape(-1, 3)), _f32c(normals.reshape(-1, 3)), _f32c(dirs.reshape(-1, 3))
     li = _i32c(light_idx)
@@ -220,6 +232,8 @@ class SecondaryStages:
         self.keep = []
         dev = surf_xyz.device
         self.cfg = march_cfg(model, table=equal_z_table(n_sample, near, far, dev), keep=self.keep)
+        if lean_counters(model):
+            self.cfg.flags |= _lib.MARCH_LEAN_COUNTERS
         self.mlp_s = mlp_struct(model, "renderModule", self.keep, light="index")
         self.sx, self.nr, self.dr = _f32c(surf_xyz.reshape(-1, 3)), _f32c(normals.reshape(-1, 3)), _f32c(dirs.reshape(-1, 3))
         self.li = _i32c(light_idx)

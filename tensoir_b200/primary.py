@@ -13,9 +13,9 @@ import torch
 import torch.nn.functional as F
 from torch.profiler import record_function
 
-from . import ops
+from . import ops, tail
 from . import vm_autograd as vm
-from .heads import fused_head, fused_heads
+from .heads import fused_head, fused_heads_multi
 
 
 def _segment_sum(values, ray_id, n_rays):
@@ -115,83 +115,60 @@ def _forward_relight_tail(model, rays, light_idx, white_bg, is_train, is_relight
 
     acc_map, depth_map = m["acc"], m["depth"]           # per-ray sums straight from the compositing kernel
 
-    z3 = torch.zeros(n_rays, 3, device=dev)
-    z1 = torch.zeros(n_rays, 1, device=dev)
-    rgb_map, normal_map, albedo_map = z3, z3.clone(), z3.clone()
-    roughness_map, nd_map, no_map, ac_map, rc_map = z1, z1.clone(), z1.clone(), z1.clone(), z1.clone()
-    if n_app > 0:
-      with record_function("tir::primary_app_stage"):
-        vd = viewdirs.index_select(0, r_a)
-        li = light_idx.reshape(-1).index_select(0, r_a)
-        # each head = ONE fused kernel launch (gather -> light factor -> basis -> PE -> MLP); the heads evaluated at
-        # the same points share one backward scatter into the appearance factors (heads.py)
-        if not is_relight:
-            rgb = fused_head(model, "renderModule", x_a, vd, li, light="index")
-            rgb_map = _segment_sum(w_a[:, None] * rgb, r_a, n_rays)
-        else:
-            group = [("renderModule", vd, li, "index"), ("renderModule_brdf", x_a, None, "mean")]
-            if model.normals_kind != "purely_derived":
-                group.append(("renderModule_normal", x_a, None, "mean"))
-            res = fused_heads(model, x_a, group)
-            rgb, brdf = res[0], res[1]
-            v_alb, v_rough = brdf[..., :3], (brdf[..., 3:4] * 0.9 + 0.09)
-            # device-side draw, same shape/order as torch.randn_like(xyz_sampled[app_mask]) (tensorBase:937)
-            draw = model.__dict__.get("_tir_randn_like")       # test hook: replay the oracle's CPU stream
-            x_j = x_a + (draw(x_a) if draw is not None else torch.randn_like(x_a)) * 0.01
-            brdf_j = fused_head(model, "renderModule_brdf", x_j, x_j, light="mean")
-            a_cost = model.compute_relative_smoothness_loss(v_alb, brdf_j[..., :3])
-            r_cost = model.compute_relative_smoothness_loss(v_rough, brdf_j[..., 3:4] * 0.9 + 0.09)
-            zero1 = torch.zeros_like(a_cost)
-            if model.normals_kind == "purely_predicted":
-                v_n = res[2]
-                nd = no = zero1
-            elif model.normals_kind == "purely_derived":
-                v_n = _derived_normals(model, x_a)
-                nd = no = zero1
-            else:  # derived_plus_predicted
-                d_n = _derived_normals(model, x_a)
-                v_n = res[2]
-                nd = torch.sum(torch.pow(v_n - d_n, 2), dim=-1, keepdim=True)
-                no = torch.sum(vd * v_n, dim=-1, keepdim=True).clamp(min=0)
-            # all 14 per-sample channels composited with ONE segment sum: [rgb 3 | normal 3 | albedo 3 | rough 1 |
-            # albedo cost 1 | rough cost 1 | normals_diff 1 | orientation 1]
-            packed = _segment_sum(w_a[:, None] * torch.cat([rgb, v_n, v_alb, v_rough, a_cost, r_cost, nd, no], dim=-1),
-                                  r_a, n_rays)
-            rgb_map, normal_map, albedo_map = packed[:, 0:3], packed[:, 3:6], packed[:, 6:9]
-            roughness_map, ac_map, rc_map = packed[:, 9:10], packed[:, 10:11], packed[:, 11:12]
-            nd_map, no_map = packed[:, 12:13], packed[:, 13:14]
-
     def bg():
         # white_bg short-circuits the CPU coin (tensorBase:979 / :1004)
         return white_bg or (is_train and bool(torch.rand((1,)) < 0.5))
 
     if not is_relight:
+        rgb_map = torch.zeros(n_rays, 3, device=dev)
+        if n_app > 0:
+            with record_function("tir::primary_app_stage"):
+                vd = viewdirs.index_select(0, r_a)
+                li = light_idx.reshape(-1).index_select(0, r_a)
+                rgb = fused_head(model, "renderModule", x_a, vd, li, light="index")
+                rgb_map = _segment_sum(w_a[:, None] * rgb, r_a, n_rays)
         if bg():
             depth_map = depth_map + (1. - acc_map) * rays[..., -1]
             rgb_map = rgb_map + (1. - acc_map[..., None])
         return rgb_map, depth_map, None, None, None, None, acc_map, None, None, None, None, None
 
-    fresnel_map = torch.zeros_like(albedo_map).fill_(model.fixed_fresnel)
-    albedo_smoothness_loss = torch.mean(ac_map)
-    roughness_smoothness_loss = torch.mean(rc_map)
-    if bg():
-        depth_map = depth_map + (1. - acc_map) * rays[..., -1]
-        rgb_map = rgb_map + (1. - acc_map[..., None])
-        # background normal (0, 0, 1), built from device-side fills only (CUDA-graph capturable)
-        bg_normal = torch.cat([torch.zeros(2, device=dev), torch.ones(1, device=dev)])
-        normal_map = normal_map + (1 - acc_map[..., None]) * bg_normal
-        albedo_map = albedo_map + (1 - acc_map[..., None])
-        roughness_map = roughness_map + (1 - acc_map[..., None])
-        fresnel_map = fresnel_map + (1 - acc_map[..., None])
-    rgb_map = rgb_map.clamp(0, 1)
-    if rgb_map.shape[0] > 0:
-        from .relight_utils import linear2srgb_torch
-        rgb_map = linear2srgb_torch(rgb_map)
-    albedo_map = albedo_map.clamp(0, 1)
-    fresnel_map = fresnel_map.clamp(0, 1)
-    roughness_map = roughness_map.clamp(0, 1)
-    normal_map = F.normalize(normal_map, p=2, dim=-1, eps=1e-6)
-    acc_mask = acc_map > 0.5
+    packed = None
+    if n_app > 0:
+        with record_function("tir::primary_app_stage"):
+            vd = viewdirs.index_select(0, r_a)
+            li = light_idx.reshape(-1).index_select(0, r_a)
+            # each head = ONE fused kernel launch (gather -> light factor -> basis -> PE -> MLP); the heads evaluated at
+            # the same points share one backward scatter into the appearance factors (heads.py)
+            group = [("renderModule", vd, li, "index"), ("renderModule_brdf", x_a, None, "mean")]
+            if model.normals_kind != "purely_derived":
+                group.append(("renderModule_normal", x_a, None, "mean"))
+            # device-side draw, same shape/order as torch.randn_like(xyz_sampled[app_mask]) (tensorBase:937)
+            draw = model.__dict__.get("_tir_randn_like")       # test hook: replay the oracle's CPU stream
+            x_j = x_a + (draw(x_a) if draw is not None else torch.randn_like(x_a)) * 0.01
+            # all heads of the step in one autograd node: one launch each forward, ONE stacked backward chain, one
+            # appearance scatter per point set (x_a, x_j)
+            res = fused_heads_multi(model, [(h, x_a, xi, l, lt) for h, xi, l, lt in group]
+                                    + [("renderModule_brdf", x_j, x_j, None, "mean")])
+            rgb, brdf, brdf_j = res[0], res[1], res[-1]
+            if model.normals_kind == "purely_predicted":
+                v_n, d_n = res[2], None
+            elif model.normals_kind == "purely_derived":
+                v_n, d_n = _derived_normals(model, x_a), None
+            else:  # derived_plus_predicted: the predicted normal shades, the derived one supervises it
+                v_n, d_n = res[2], _derived_normals(model, x_a)
+            # BRDF split, smoothness / normal costs, weighting and all 14 per-ray sums in one kernel (tail.py)
+            packed = tail.fused_tail(w_a, r_a, rgb, brdf, brdf_j, v_n, d_n, viewdirs, n_rays)
+    if packed is None:
+        packed = torch.zeros(n_rays, tail.TAIL_CHANNELS, device=dev)
+    if n_rays == 0:        # torch.mean over zero rays is NaN in the reference; keep that contract on the empty batch
+        z3, z1 = torch.zeros(0, 3, device=dev), torch.zeros(0, 1, device=dev)
+        nan = torch.full((), float("nan"), device=dev)
+        return (z3, depth_map, z3.clone(), z3.clone(), z1, z3.clone(), acc_map, z1.clone(), z1.clone(), acc_map > 0.5,
+                nan, nan.clone())
+    # background compositing, clamps, sRGB, normal normalisation, acc_mask and the two scalar means: one kernel
+    (rgb_map, depth_map, normal_map, albedo_map, roughness_map, fresnel_map, nd_map, no_map, acc_mask,
+     albedo_smoothness_loss, roughness_smoothness_loss) = tail.epilogue(packed, acc_map, depth_map, rays,
+                                                                        model.fixed_fresnel, bg())
     return (rgb_map, depth_map, normal_map, albedo_map, roughness_map, fresnel_map, acc_map, nd_map, no_map,
             acc_mask, albedo_smoothness_loss, roughness_smoothness_loss)
 

@@ -13,6 +13,14 @@ from . import vm_autograd
 from .tensorbase import TensorBase, AlphaGridMask, raw2alpha  # noqa: F401  (re-exported like the reference)
 
 
+def _channel_last_param(values, device=None):
+    """nn.Parameter with the reference's logical shape [1,C,H,W] whose STORAGE is channel-last ([H][W][C]): the layout
+    the kernels index, so they read the parameter itself (device_field.py) and their channel-last gradient buffers are
+    accepted by autograd without a copy.  Same random values / state_dict contents as the reference layout."""
+    t = values if device is None else values.to(device)
+    return torch.nn.Parameter(t.contiguous(memory_format=torch.channels_last))
+
+
 class TensorVMSplit(TensorBase):
     def __init__(self, aabb, gridSize, device, **kargs):
         super().__init__(aabb, gridSize, device, **kargs)
@@ -29,10 +37,10 @@ class TensorVMSplit(TensorBase):
         for i in range(len(self.vecMode)):
             vec_id = self.vecMode[i]
             mat_id_0, mat_id_1 = self.matMode[i]
-            plane_coef.append(torch.nn.Parameter(
-                scale * torch.randn((1, n_component[i], gridSize[mat_id_1], gridSize[mat_id_0]))))
-            line_coef.append(torch.nn.Parameter(scale * torch.randn((1, n_component[i], gridSize[vec_id], 1))))
-        return torch.nn.ParameterList(plane_coef).to(device), torch.nn.ParameterList(line_coef).to(device)
+            plane_coef.append(_channel_last_param(
+                scale * torch.randn((1, n_component[i], gridSize[mat_id_1], gridSize[mat_id_0])), device))
+            line_coef.append(_channel_last_param(scale * torch.randn((1, n_component[i], gridSize[vec_id], 1)), device))
+        return torch.nn.ParameterList(plane_coef), torch.nn.ParameterList(line_coef)
 
     def get_optparam_groups(self, lr_init_spatialxyz=0.02, lr_init_network=0.001):
         """tensoRF_rotated_lights.py:33-57 (general variant :45-46)."""
@@ -120,7 +128,7 @@ class TensorVMSplit(TensorBase):
     # Both operations REBIND the Parameters (the train loop rebuilds Adam afterwards, train_tensoIR.py:421-422);
     # DeviceField notices the new (data_ptr, version, shape) and rebuilds the kernel-side shadows.
     def _rebind(self, plist, k, tensor):
-        plist[k] = torch.nn.Parameter(tensor)
+        plist[k] = _channel_last_param(tensor)
 
     @torch.no_grad()
     def up_sampling_VM(self, plane_coef, line_coef, res_target):

@@ -33,11 +33,15 @@ def test_struct_sizes_match_header(lib):
     from tensoir_b200 import _lib
     assert (ctypes.sizeof(_lib.TirField), ctypes.sizeof(_lib.TirMlp), ctypes.sizeof(_lib.TirMarchCfg)) == (224, 88, 48)
     assert _lib.APP_SAMPLE_BYTES == 24
+    assert ctypes.sizeof(_lib.TirRayMaps) == 64
 
 
 def test_null_arguments_are_rejected(lib):
     assert lib.tir_pack_channels_last(None, None, 1, 1, 1, None) == -1
     assert lib.tir_density_points(None, None, 5, None, None, None) == -1
+    assert lib.tir_tail_fwd(5, None, None, None, None, None, None, None, None, None, None) == -1
+    assert lib.tir_epilogue_fwd(5, None, None, None, None, 0.04, 1, None, None, None, None) == -1
+    assert lib.tir_tail_fwd(0, None, None, None, None, None, None, None, None, None, None) == 0      # empty: no-op
     assert lib.tir_density_points(None, None, 0, None, None, None) == 0      # empty input is a no-op, not an error
 
 
@@ -199,3 +203,23 @@ def test_lr_decay_under_captured_step_host_logic():
     st.opt = torch.optim.SGD([p], lr=0.1)
     with pytest.raises(TypeError):
         st.scale_lr(0.5)
+
+
+def test_channel_last_parameters_need_no_shadow(golden_rotated):
+    """VM factors are stored channel-last (NCHW-shaped views): DeviceField hands the kernels the parameter's own
+    storage, state_dict values / shapes are the reference's, and a DP gradient bucket view has the same strides."""
+    from gpu_helpers import model_from_fixture
+    from tensoir_b200 import _lib, device_field
+    from tensoir_b200.dp import GradBucket
+    m = model_from_fixture(golden_rotated, "cpu")
+    df = device_field.DeviceField()
+    for p in list(m.density_plane) + list(m.app_line):
+        assert p.is_contiguous(memory_format=torch.channels_last)
+        view = df._pack(_lib.load(), p)
+        assert view.data_ptr() == p.data_ptr() and view.is_contiguous() and view.shape == (p.shape[2], p.shape[3], p.shape[1])
+        assert torch.equal(view.permute(2, 0, 1)[None], p.detach())
+    for k, v in golden_rotated["state_dict"].items():
+        assert torch.equal(m.state_dict()[k], v), k
+    bucket = GradBucket(m.parameters())
+    for p, v in zip(bucket.params, bucket.views):
+        assert v.shape == p.shape and v.stride() == p.stride()

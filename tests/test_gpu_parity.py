@@ -497,3 +497,115 @@ def test_config3_128_secondary_directions(golden_rotated):
         want = O.renderer_train(f, fx["rays"], fx["light_idx"], -1, True, False, True, method, 160000, 32)
         for k in ("rgb_with_brdf_map", "rgb_map", "normal_map", "acc_map"):
             close(got[k], want[k], TOL, f"{method}:{k}")
+
+
+def test_lean_counter_mode_is_bit_identical(rot):
+    """TIR_MARCH_LEAN_COUNTERS (production mode): skipping the rest of a ray whose transmittance is exactly 0 changes no
+    output beyond summation-order noise, no appearance sample and no ray count; only the mask / density counters shrink."""
+    from tensoir_b200 import ops
+    fx, m = rot
+    pts, dirs, li = fx["surf"].to(DEV), fx["dirs"].to(DEV), fx["li2"].to(DEV)
+    table = ops.equal_z_table(96, 0.05, 1.5, DEV)
+    res = []
+    for lean in (False, True):
+        m.__dict__["_tir_lean"] = lean
+        cnt = ops.new_counters(DEV)
+        t, a, d, rgb, sc = ops.march_radiance(m, pts, dirs, li, table=table, counters=cnt)
+        lst = sc.samples()
+        order = torch.argsort(lst["ray"].long() * 4096 + lst["sample"].long())
+        res.append((t, a, d, rgb, {k: v[order] for k, v in lst.items()}, ops.counters_dict(cnt)))
+    m.__dict__.pop("_tir_lean")
+    (t0, a0, d0, r0, l0, c0), (t1, a1, d1, r1, l1, c1) = res
+    # skipped samples carry weight exactly 0; what may move is the association of the warp scans (the gather batches are
+    # composed differently), i.e. the last bit
+    close(t0, t1, 1e-6, "t_last"), close(a0, a1, 1e-6, "acc"), close(d0, d1, 1e-6, "depth"), close(r0, r1, 1e-6, "rgb")
+    for k in ("ray", "sample"):
+        assert torch.equal(l0[k], l1[k]), k         # the appearance list is the same set of samples
+    close(l0["weight"], l1["weight"], 1e-6, "weight")
+    assert c0["rays"] == c1["rays"] and c0["app"] == c1["app"]
+    assert c1["mask"] <= c0["mask"] and c1["density"] <= c0["density"]
+
+
+def _torch_tail(w, ray, rgb, brdf, brdfj, vn, dn, viewdirs, n_rays, model):
+    """The torch expressions the fused tail replaces (tensorBase_rotated_lights.py:930-975)."""
+    v_alb, v_rough = brdf[..., :3], brdf[..., 3:4] * 0.9 + 0.09
+    a_cost = model.compute_relative_smoothness_loss(v_alb, brdfj[..., :3])
+    r_cost = model.compute_relative_smoothness_loss(v_rough, brdfj[..., 3:4] * 0.9 + 0.09)
+    vd = viewdirs.index_select(0, ray)
+    if dn is not None:
+        nd = torch.sum(torch.pow(vn - dn, 2), dim=-1, keepdim=True)
+        no = torch.sum(vd * vn, dim=-1, keepdim=True).clamp(min=0)
+    else:
+        nd = no = torch.zeros_like(a_cost)
+    vals = torch.cat([rgb, vn, v_alb, v_rough, a_cost, r_cost, nd, no], dim=-1)
+    return torch.zeros(n_rays, 14, device=w.device).index_add_(0, ray, w[:, None] * vals)
+
+
+def _torch_epilogue(packed, acc, depth, rays, fresnel0, bg):
+    """The per-ray end of TensorBase.forward in torch (tensorBase_rotated_lights.py:977-1036)."""
+    from tensoir_b200.relight_utils import linear2srgb_torch
+    rgb, normal, albedo = packed[:, 0:3], packed[:, 3:6], packed[:, 6:9]
+    rough, ac, rc, nd, no = packed[:, 9:10], packed[:, 10:11], packed[:, 11:12], packed[:, 12:13], packed[:, 13:14]
+    fres = torch.zeros_like(albedo).fill_(fresnel0)
+    if bg:
+        depth = depth + (1. - acc) * rays[..., -1]
+        rgb = rgb + (1. - acc[..., None])
+        normal = normal + (1 - acc[..., None]) * torch.tensor([0., 0., 1.], device=packed.device)
+        albedo, rough, fres = albedo + (1 - acc[..., None]), rough + (1 - acc[..., None]), fres + (1 - acc[..., None])
+    return (linear2srgb_torch(rgb.clamp(0, 1)), depth, torch.nn.functional.normalize(normal, p=2, dim=-1, eps=1e-6),
+            albedo.clamp(0, 1), rough.clamp(0, 1), fres.clamp(0, 1), nd, no, acc > 0.5, ac.mean(), rc.mean())
+
+
+@pytest.mark.parametrize("both", [True, False])
+def test_fused_tail_kernel_vs_autograd(rot, both):
+    from tensoir_b200 import tail
+    _, m = rot
+    torch.manual_seed(3)
+    n, n_rays = 5000, 512
+    ray = torch.sort(torch.randint(0, n_rays, (n,), device=DEV))[0]
+    w = torch.rand(n, device=DEV) * 0.3
+    w[::17] = 0.0                                                        # padding rows of a static-capacity list
+    rgb, brdf, brdfj = torch.rand(n, 3, device=DEV), torch.rand(n, 4, device=DEV), torch.rand(n, 4, device=DEV)
+    vn = torch.nn.functional.normalize(torch.randn(n, 3, device=DEV), dim=-1)
+    dn = torch.nn.functional.normalize(torch.randn(n, 3, device=DEV), dim=-1) if both else None
+    vd = torch.nn.functional.normalize(torch.randn(n_rays, 3, device=DEV), dim=-1)
+    G = torch.randn(n_rays, 14, device=DEV)
+    res = []
+    for fn in (lambda *a: tail.fused_tail(*a), lambda *a: _torch_tail(*a, m)):
+        leaves = [t.clone().requires_grad_(True) for t in (w, rgb, brdf, brdfj, vn)] + \
+                 ([dn.clone().requires_grad_(True)] if both else [])
+        out = fn(leaves[0], ray, leaves[1], leaves[2], leaves[3], leaves[4], leaves[5] if both else None, vd, n_rays)
+        out.backward(G)
+        res.append([out.detach()] + [l.grad for l in leaves])
+    for k, (g, wnt) in enumerate(zip(*res)):
+        close(g, wnt, 2e-4, f"tail[{k}]")
+
+
+@pytest.mark.parametrize("bg", [True, False])
+def test_fused_epilogue_kernel_vs_autograd(rot, bg):
+    from tensoir_b200 import tail
+    torch.manual_seed(9)
+    n = 2048
+    packed = torch.rand(n, 14, device=DEV) * 1.3 - 0.1                    # some channels outside [0,1]: clamp gates
+    packed[:100, 0:3] *= 0.002                                           # linear branch of the sRGB curve
+    acc = torch.rand(n, device=DEV)
+    acc[100:200] = 1.0
+    depth, rays = torch.rand(n, device=DEV) * 4, torch.randn(n, 6, device=DEV)
+    gs = None
+    res = []
+    for fn in (tail.epilogue, _torch_epilogue):
+        leaves = [t.clone().requires_grad_(True) for t in (packed, acc, depth)]
+        outs = fn(leaves[0], leaves[1], leaves[2], rays, 0.04, bg)
+        # the fresnel map is a constant when no background is composited: no gradient to compare
+        diff = [o for k, o in enumerate(outs) if o.dtype != torch.bool and (bg or k != 5)]
+        if gs is None:
+            gs = [torch.randn_like(o) for o in diff]
+        torch.autograd.backward(diff, gs)
+        res.append((outs, [l.grad if l.grad is not None else torch.zeros_like(l) for l in leaves]))
+    for k, (g, wnt) in enumerate(zip(res[0][0], res[1][0])):
+        if g.dtype == torch.bool:
+            assert torch.equal(g, wnt)
+        else:
+            close(g, wnt.reshape(g.shape), 1e-4, f"epilogue out[{k}]")
+    for k, (g, wnt) in enumerate(zip(res[0][1], res[1][1])):
+        close(g, wnt, 2e-3, f"epilogue grad[{k}]")
