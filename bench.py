@@ -290,7 +290,9 @@ def main():
         from tensoir_b200.static_step import StaticTrainStep
         graphed = StaticTrainStep(model, opt, per_rank, n_s, Args, lambda ret, m: loss_of(ret, target, m),
                                   grad_bucket=bucket, device=dev)
-        caps = graphed.calibrate(host_batches[:8])     # max over 8 batches x 1.2 headroom; overflow is counted
+        # lists sized from 8 batches x 1.5; they grow by themselves (high-water marks, re-capture) and a replay whose
+        # lists did not fit is an exact no-op that is redone (static_step.py) - never a silently different step
+        graphed.calibrate(host_batches[:8])
         graphed.capture(warmup=3)
 
     def step(rays, li):
@@ -328,6 +330,8 @@ def main():
         barrier()
         torch.cuda.profiler.stop()
         ms = e0.elapsed_time(e1)
+        if graphed is not None:
+            graphed.flush()                       # settle the last replays: overflowed ones would be redone here
         t = torch.tensor([ms], device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -340,9 +344,12 @@ def main():
     dev_batches = [(r.to(dev), l.to(dev)) for r, l in host_batches[:total]]
     for rays, li in dev_batches[:a.warmup]:
         step(rays, li)
+    if graphed is not None:
+        graphed.flush()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    events0 = (graphed.redone, graphed.recaptures) if graphed is not None else (0, 0)
     ms, cnt, launches = timed_region(dev_batches[a.warmup:], read_loss=False)
     rays_total = cnt["rays"]          # TIR_CNT_RAYS counts every marched ray: primary (valid-list pass) + secondary
     value = rays_total / (ms * 1e-3)
@@ -353,9 +360,24 @@ def main():
     ms_e2e, cnt_e2e, _ = timed_region(pinned[total + a.warmup:2 * total], read_loss=True)
     clk = clocks.stop() if rank == 0 else None
     e2e_value = cnt_e2e["rays"] / (ms_e2e * 1e-3)
+    events1 = (graphed.redone, graphed.recaptures) if graphed is not None else (0, 0)
     overflow = graphed.overflowed() if graphed is not None else 0
+    caps = graphed.capacities() if graphed is not None else None
     if graphed is not None:
         graphed.release()
+    bad = torch.tensor([float(events1 != events0 or overflow > 0)], device=dev)
+    if world > 1:
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+    if bad.item() > 0:
+        # a timed replay overflowed its static lists (it was a no-op and was redone) or the graph had to be re-captured
+        # inside the timed region: the K timed steps are not K clean steps -> no number
+        sys.stderr.write(f"bench: static lists overflowed / re-captured inside the timed region on rank {rank} "
+                         f"(redone, recaptures) {events0} -> {events1}, overflowed replays {overflow}; no result\n")
+        sys.stderr.flush()
+        if world > 1:
+            torch.cuda.synchronize()
+            dist.barrier()
+        os._exit(3)
 
     def finish():
         """Leave together: a CUDA graph holding NCCL kernels plus communicator teardown can hang at interpreter exit,
@@ -387,7 +409,8 @@ def main():
                              "units_per_launch are the reference algorithm's counts from an instrumented launch",
             "gpu_launches": launches, "clocks": clk, "roofline": roof,
             "execution": ("eager" if a.eager else f"cuda-graph replay of the whole step (static list capacities "
-                          f"{caps}, overflowed steps: {overflow})")}
+                          f"{caps}, overflowed steps: {overflow}, redone: {events1[0]}, re-captures during warm-up: "
+                          f"{events1[1]}; an overflowed replay is a device-side no-op that is redone with larger lists)")}
     if not a.no_cpu_baseline and world == 1:
         cb = cpu_baseline(a, steps=2, warmup=1)
         line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": "port",

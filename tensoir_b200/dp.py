@@ -22,13 +22,16 @@ class GradBucket:
     """Persistent flat fp32 gradient bucket; ``p.grad`` of every parameter becomes a view into it, so the
     all-reduce needs no per-step flatten / unflatten copies.  Rebuild after shrink / upsample (new Parameters)."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter]):
+    def __init__(self, params: Iterable[torch.nn.Parameter], extra: int = 1):
         self.params = _params_with_grad(params)
         if not self.params:
             raise ValueError("no parameters")
         dev = self.params[0].device
         n = sum(p.numel() for p in self.params)
-        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        # `extra` spare floats at the end ride along with the gradients in the same all-reduce (the CUDA-graph step
+        # puts its list-overflow flag there, so that one rank's overflow makes every rank skip the same update)
+        self.flat = torch.zeros(n + extra, dtype=torch.float32, device=dev)
+        self.extra = self.flat[n:]
         o = 0
         self.views = []
         for p in self.params:
@@ -48,6 +51,7 @@ class GradBucket:
         for p, v in zip(self.params, self.views):
             if p.grad is None:
                 v.zero_()
+                p.grad = v          # every rank must apply the averaged gradient, also one whose batch produced none
             elif p.grad.data_ptr() != v.data_ptr():
                 v.copy_(p.grad)
                 p.grad = v

@@ -194,14 +194,33 @@ def secondary_radiance(model, surf_xyz, normals, light_idx, dirs, *, n_sample=96
     ind = torch.zeros(n_pts, n_dirs, 3, device=dev)
     if n_pts == 0:
         return vis, ind, None
-    cap = capacity if capacity is not None else max(1 << 16, 4 * n_pts * n_dirs)
-    sc = _scratch(model, dev, cap)
-    _lib.check(lib.tir_secondary_radiance(C.byref(f), C.byref(mlp), _lib.dptr(sx), _lib.dptr(nr),
-                                          _lib.dptr(li, torch.int32), n_pts, _lib.dptr(dr), n_dirs, C.byref(cfg),
-                                          _lib.dptr(vis), _lib.dptr(ind), _lib.dptr(sc.buf, torch.uint8),
-                                          _lib.dptr(sc.count, torch.int32), sc.capacity,
-                                          None if counters is None else _lib.dptr(counters, torch.int64),
-                                          _lib.stream_ptr()), "tir_secondary_radiance")
+    st = model.__dict__.get("_tir_static")
+    per_slot = 4 if st is None else int(st.get("sec_per_slot", 4))
+    cap = capacity if capacity is not None else max(1 << 16, per_slot * n_pts * n_dirs)
+    while True:
+        sc = _scratch(model, dev, cap)
+        _lib.check(lib.tir_secondary_radiance(C.byref(f), C.byref(mlp), _lib.dptr(sx), _lib.dptr(nr),
+                                              _lib.dptr(li, torch.int32), n_pts, _lib.dptr(dr), n_dirs, C.byref(cfg),
+                                              _lib.dptr(vis), _lib.dptr(ind), _lib.dptr(sc.buf, torch.uint8),
+                                              _lib.dptr(sc.count, torch.int32), sc.capacity,
+                                              None if counters is None else _lib.dptr(counters, torch.int64),
+                                              _lib.stream_ptr()), "tir_secondary_radiance")
+        if st is not None:
+            # shape-static mode (CUDA-graph capture): no host sync; the step's overflow flag turns an overflowed step
+            # into a no-op that the host redoes with a larger scratch list (static_step.py)
+            from .primary import note_count
+            note_count(st, 3, sc.count[0], sc.capacity)
+            break
+        need = int(sc.count.item())        # the march counts every appearance sample, also those it could not store
+        if need <= sc.capacity:
+            break
+        # the list was too short: samples were dropped -> redo with a list that fits (never silently lose samples)
+        if counters is not None:
+            raise _lib.TirError(f"secondary appearance list overflowed ({need} > {sc.capacity}) while counters are "
+                                f"being accumulated; pass capacity >= {need}")
+        cap = need + (need >> 3)
+        vis.zero_()
+        ind.zero_()
     return vis, ind, sc
 
 

@@ -27,6 +27,16 @@ def _segment_sum(values, ray_id, n_rays):
     return out.index_add_(0, ray_id, values)
 
 
+def note_count(st, slot, count, cap):
+    """Shape-static mode bookkeeping, all on the device: remember the real length of list ``slot`` (0 valid samples,
+    1 appearance samples, 2 surface hits, 3 secondary appearance scratch) for the host's high-water check and raise the
+    step's overflow flag when it exceeds the static capacity (static_step.py: an overflowed step is turned into an
+    exact no-op and redone with larger lists)."""
+    count = count.to(torch.int64)
+    st["stats"][slot].copy_(count)
+    st["overflow_step"].add_((count > cap).to(torch.int64))
+
+
 def any_sample_in_mask(model, rays_o, rays_d, n_samples):
     """(alphaMask.sample_alpha(xyz_sampled) > 0).any(-1) of filtering_rays (tensorBase:803-804)."""
     res = vm.valid_samples(model, rays_o, rays_d, n_samples=n_samples, no_bbox=True, count_only=True)
@@ -64,7 +74,7 @@ def march(model, rays, is_train, n_samples, counters=None):
     lst = vm.valid_samples(model, rays[:, :3], rays[:, 3:6], n_samples=n_samples, jitter=jitter, counters=counters,
                            capacity=None if st is None else st["cap_valid"])
     if st is not None:
-        st["overflow"] += lst["overflow"].to(st["overflow"].dtype)
+        note_count(st, 0, lst["offsets"][-1], st["cap_valid"])
     ray_id = lst["ray"].long()
     if lst["xn"].shape[0] > 0:
         feat = vm.density_feature(model, lst["xn"])
@@ -106,7 +116,7 @@ def _forward_relight_tail(model, rays, light_idx, white_bg, is_train, is_relight
         app_idx = app_idx.clamp(min=0)
         n_app = st["cap_app"]
         n_real = app_sel.sum()
-        st["overflow"] += (n_real > st["cap_app"]).to(st["overflow"].dtype)
+        note_count(st, 1, n_real, st["cap_app"])
         if cnt is not None:
             cnt[2] += n_real
         w_a = weight.index_select(0, app_idx) * real.to(weight.dtype)

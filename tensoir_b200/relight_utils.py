@@ -131,3 +131,116 @@ def _shade(tensoIR, normal_map, albedo_map, roughness_map, fresnel_map, surf2c, 
     if use_linear2srgb and rgb_with_brdf.shape[0] > 0:
         rgb_with_brdf = linear2srgb_torch(rgb_with_brdf)
     return rgb_with_brdf
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Rest of the module surface the reference's data loaders / scripts import from models.relight_utils
+# (dataLoader/tensoIR_rotation_setting.py:13, scripts/relight_importance.py:21-24)
+# ---------------------------------------------------------------------------------------------------------------------
+def grid_sample(image, optical):
+    """Differentiable bilinear sampler with CLAMPED tap indices and unclamped weights (relight_utils.py:57-107): the
+    sampler compute_densityfeature_with_xyz_grad differentiates twice.  image [N,C,IH,IW], optical [N,H,W,2] in
+    [-1,1] (align_corners=True convention) -> [N,C,H,W].  The hot path evaluates this analytically in
+    csrc/tir_vm.cu (tir_vm_density_grad); this tensor version serves callers that use it directly."""
+    N, C, IH, IW = image.shape
+    _, H, W, _ = optical.shape
+    x = (optical[..., 0] + 1) * 0.5 * (IW - 1)
+    y = (optical[..., 1] + 1) * 0.5 * (IH - 1)
+    with torch.no_grad():
+        x0, y0 = torch.floor(x), torch.floor(y)
+    fx, fy = x - x0, y - y0                               # weights come from the UNclamped corners
+    flat = image.reshape(N, C, IH * IW)
+
+    def tap(dx, dy):
+        with torch.no_grad():
+            xi = (x0 + dx).clamp(0, IW - 1)
+            yi = (y0 + dy).clamp(0, IH - 1)
+            idx = (yi * IW + xi).long().view(N, 1, H * W).expand(N, C, H * W)
+        return torch.gather(flat, 2, idx).view(N, C, H, W)
+    w00, w10 = ((1 - fx) * (1 - fy)).view(N, 1, H, W), (fx * (1 - fy)).view(N, 1, H, W)
+    w01, w11 = ((1 - fx) * fy).view(N, 1, H, W), (fx * fy).view(N, 1, H, W)
+    return tap(0, 0) * w00 + tap(1, 0) * w10 + tap(0, 1) * w01 + tap(1, 1) * w11
+
+
+def _clip_0to1_warn_torch(tensor_0to1):
+    """relight_utils.py:518-533 (the warning is dropped: clamp is the identity on in-range data, no host sync)."""
+    if isinstance(tensor_0to1, torch.Tensor):
+        return torch.clamp(tensor_0to1, min=0, max=1)
+    if isinstance(tensor_0to1, np.ndarray):
+        return np.clip(tensor_0to1, 0, 1)
+    raise NotImplementedError(f'Do not support dtype {type(tensor_0to1)}')
+
+
+def _convert_sph_conventions(pts_r_angle1_angle2, what2what):
+    """relight_utils.py:537-567: (r, lat, lng) <-> (r, theta, phi)."""
+    p = np.asarray(pts_r_angle1_angle2)
+    out = np.zeros(p.shape)
+    out[:, 0] = p[:, 0]
+    out[:, 1] = np.pi / 2 - p[:, 1]
+    if what2what == 'lat-lng_to_theta-phi':
+        out[:, 2] = np.where(p[:, 2] < 0, 2 * np.pi + p[:, 2], p[:, 2])
+    elif what2what == 'theta-phi_to_lat-lng':
+        out[:, 2] = np.where(p[:, 2] > np.pi, p[:, 2] - 2 * np.pi, p[:, 2])
+    else:
+        raise NotImplementedError(what2what)
+    return out
+
+
+def sph2cart(pts_sph, convention='lat-lng'):
+    """relight_utils.py:570-595."""
+    pts_sph = np.asarray(pts_sph)
+    assert pts_sph.ndim == 2 and pts_sph.shape[-1] == 3, "Shape of input mush be (n, 3)"
+    assert (np.abs(pts_sph[:, 1:]) <= 2 * np.pi).all(), "Input degree falls out of [-2pi, 2pi]"
+    if convention == 'theta-phi':
+        pts_sph = _convert_sph_conventions(pts_sph, 'theta-phi_to_lat-lng')
+    elif convention != 'lat-lng':
+        raise NotImplementedError(convention)
+    r, lat, lng = pts_sph[:, 0], pts_sph[:, 1], pts_sph[:, 2]
+    return np.stack((r * np.cos(lat) * np.cos(lng), r * np.cos(lat) * np.sin(lng), r * np.sin(lat)), axis=-1)
+
+
+@torch.no_grad()
+def sample_ray_equally(tensoIR, rays_o, rays_d, nSample=-1, vis_near=0.03, vis_far=1.5, device=None):
+    """relight_utils.py:707-722 as tensors (the fused marches generate these samples on chip; this form is for callers
+    that want the points themselves) -> (rays_pts [N,S,3], z_vals [1,S], in-aabb mask [N,S])."""
+    z_vals = ops.equal_z_table(nSample, vis_near, vis_far, rays_o.device).unsqueeze(0)
+    rays_pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals.view(1, -1, 1)
+    aabb = tensoIR.aabb.to(rays_o.device)
+    outside = ((aabb[0] > rays_pts) | (rays_pts > aabb[1])).any(dim=-1)
+    return rays_pts, z_vals, ~outside
+
+
+def _pairs(pts, light_xyz):
+    surf2light = safe_l2_normalize(light_xyz[None, :, :] - pts[:, None, :], dim=-1)
+    return pts.unsqueeze(1).expand(-1, light_xyz.shape[0], -1).reshape(-1, 3), surf2light.reshape(-1, 3)
+
+
+@torch.no_grad()
+def compute_visibility(tensoIR, pts, light_xyz, nSample, vis_near, vis_far, args, device='cuda'):
+    """relight_utils.py:617-655: visibility of every (surface point, light position) pair -> [N, n_lights, 1].
+    One fused density march over all pairs (no 81920-ray chunk loop: nothing [rays, samples]-shaped exists)."""
+    surface_pts, surf2light = _pairs(pts, light_xyz)
+    nerv_vis, nerfactor_vis = compute_transmittance(tensoIR, surface_pts, surf2light, nSample, vis_near, vis_far)
+    vis = nerv_vis if args.vis_equation == 'nerv' else nerfactor_vis
+    return vis.reshape(-1, light_xyz.shape[0], 1)
+
+
+@torch.no_grad()
+def compute_visibility_and_indirect_light(tensoIR, pts, light_xyz, light_idx, nSample, vis_near, vis_far, args,
+                                          device='cuda'):
+    """relight_utils.py:727-775 -> (visibility [N, n_lights, 1], indirect_light [N, n_lights, 3])."""
+    surface_pts, surf2light = _pairs(pts, light_xyz)
+    li = light_idx.view(-1, 1, 1).expand((-1, light_xyz.shape[0], 1)).reshape(-1, 1)
+    nerv_vis, nerfactor_vis, indirect = compute_radiance(tensoIR, surface_pts, surf2light, li, nSample, vis_near,
+                                                         vis_far)
+    vis = nerv_vis if args.vis_equation == 'nerv' else nerfactor_vis
+    return vis.reshape(-1, light_xyz.shape[0], 1), indirect.reshape(-1, light_xyz.shape[0], 3)
+
+
+def __getattr__(name):
+    # read_hdr / Environment_Light live next to the relighting driver (tensoir_b200/relight.py, which imports this
+    # module); resolved lazily to keep the import graph acyclic
+    if name in ("read_hdr", "Environment_Light"):
+        from . import relight
+        return getattr(relight, name)
+    raise AttributeError(name)

@@ -29,7 +29,8 @@ def Renderer_TensoIR_train(rays=None, normal_gt=None, light_idx=None, tensoIR=No
         cap = min(int(st.get("cap_hit", n)), n) if n > 0 else 0
         idx = torch.nonzero_static(acc_mask, size=cap, fill_value=-1).reshape(-1)
         real = idx >= 0
-        st["overflow"] += (acc_mask.sum() > cap).to(st["overflow"].dtype)
+        from .primary import note_count
+        note_count(st, 2, acc_mask.sum(), cap)
         src = idx.clamp(min=0)
         keep = real[:, None].to(normal_map.dtype)
         shaded = render_with_BRDF(depth_map.index_select(0, src), normal_map.index_select(0, src) * keep,

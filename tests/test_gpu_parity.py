@@ -315,13 +315,16 @@ def test_static_capacity_mode_matches_dynamic(golden_rotated):
             jit = torch.rand(64, 1)
             dirs = m.gen_light_incident_dirs(method='stratified_sampling')
             m.__dict__["_tir_static"] = {"cap_valid": 64 * 60, "cap_app": 1024, "cap_hit": 60, "jitter": jit.to(DEV),
-                                         "dirs": dirs.to(DEV), "overflow": torch.zeros((), dtype=torch.int64, device=DEV)}
+                                         "dirs": dirs.to(DEV), "overflow": torch.zeros((), dtype=torch.int64, device=DEV),
+                                         "stats": torch.zeros(4, dtype=torch.int64, device=DEV),
+                                         "overflow_step": torch.zeros((), dtype=torch.int64, device=DEV)}
         got = Renderer_TensoIR_train(rays, None, li, m, N_samples=60, white_bg=True, is_train=True, is_relight=True,
                                      sample_method='stratified_sampling', device=DEV, args=renderer_args(24))
         loss = _train_loss(got)
         loss.backward()
         if static:
-            assert int(m.__dict__["_tir_static"]["overflow"]) == 0
+            assert int(m.__dict__["_tir_static"]["overflow_step"]) == 0
+            assert int(m.__dict__["_tir_static"]["stats"][0]) > 0          # real list lengths are recorded
         outs.append((got, loss, {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}))
     (g0, l0, gr0), (g1, l1, gr1) = outs
     for k in g0:
@@ -347,12 +350,54 @@ def test_cuda_graph_step(golden_rotated):
     st.calibrate([(rays, li)])
     before = m.density_plane[0].detach().clone()
     st.capture(warmup=2)
+    assert torch.equal(m.density_plane[0].detach(), before)        # capture()'s warm-up executions do not train
     losses = [float(st.run(rays, li)) for _ in range(4)]
+    st.flush()
     assert all(l == l and l < 10 for l in losses), losses
-    assert st.overflowed() == 0
+    assert st.overflowed() == 0 and st.redone == 0
     assert float((m.density_plane[0] - before).abs().max()) > 0
     assert losses[-1] < losses[0] + 0.05          # Adam on a fixed batch does not diverge
     st.release()
+
+
+def test_cuda_graph_step_overflow_is_redone(golden_rotated):
+    """Lists that are too short never change the computation: the overflowed replay leaves parameters and Adam state
+    untouched (found_inf), the host grows the lists, re-captures and redoes the batch; the result equals a run whose
+    lists were large enough from the start (up to atomics order / the padded xyz-noise stream)."""
+    from tensoir_b200.static_step import StaticTrainStep
+    fx = golden_rotated
+    rays, li = fx["rays"].to(DEV), fx["light_idx"].to(DEV)
+    outs = []
+    for tiny in (False, True):
+        m = model_from_fixture(fx, DEV)
+        m.__dict__["_tir_randn_like"] = lambda t: torch.sin(t * 977.0)      # noise independent of the padding
+        opt = torch.optim.Adam(m.get_optparam_groups(0.02, 0.001), betas=(0.9, 0.99), fused=True, capturable=True)
+        st = StaticTrainStep(m, opt, 64, 60, renderer_args(24), lambda ret, mm: _train_loss(ret), device=DEV, lag=1)
+        st.calibrate([(rays, li)])
+        fixed_dirs = m.gen_light_incident_dirs(method='fixed_envirmap')
+
+        def stage(slot, st=st, fixed_dirs=fixed_dirs):       # identical host "randoms" in both runs and in the redo
+            st.static["jitter"].fill_(0.5)
+            st.static["dirs"].copy_(fixed_dirs)
+        st._stage_host_randoms = stage
+        if tiny:
+            st._set_caps(max(64, st.static["cap_valid"] // 8), max(16, st.static["cap_app"] // 8), 4)
+        st.capture(warmup=1)
+        torch.manual_seed(5)
+        for _ in range(3):
+            st.run(rays, li)
+        st.flush()
+        if tiny:
+            assert st.redone >= 1 and st.recaptures >= 1
+        else:
+            assert st.redone == 0 and st.overflowed() == 0
+        steps = {int(v["step"].item()) for v in opt.state.values()}
+        assert steps == {3}, steps                        # no-op replays did not advance Adam's step counters
+        outs.append((m.renderModule.mlp[0].weight.detach().clone(), m.density_plane[0].detach().clone()))
+        st.release()
+    (w0, d0), (w1, d1) = outs
+    assert float((w0 - w1).abs().max()) < 2e-2 * float(w0.abs().max())
+    assert float((d0 - d1).abs().max()) < 2e-2 * max(float(d0.abs().max()), 1e-3)
 
 
 def test_edge_cases(golden_rotated):
