@@ -345,7 +345,9 @@ def main():
     for rays, li in dev_batches[:a.warmup]:
         step(rays, li)
     if graphed is not None:
-        graphed.flush()
+        # lists at 2x the longest seen during warm-up: growth inside the timed regions would need +60 % in 2K steps
+        graphed.reserve(2.0)
+        sys.stderr.write(f"bench: static lists {graphed.capacities()} after warm-up (seen {graphed._seen})\n")
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()

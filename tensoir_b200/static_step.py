@@ -202,6 +202,8 @@ class StaticTrainStep:
         slot["event"] = None
         caps = self.capacities()
         seen = (n_valid, n_app, n_hit)
+        old = getattr(self, "_seen", (0, 0, 0, 0))
+        self._seen = tuple(max(a, b) for a, b in zip(old, (n_valid, n_app, n_hit, n_sec)))
         want = list(caps)
         for i in range(3):
             if seen[i] > self.grow_at * caps[i] and not (i == 2 and caps[i] >= self.n_rays):
@@ -261,6 +263,22 @@ class StaticTrainStep:
         self._step += 1
         self._launch(rays, light_idx, slot)
         return self.loss
+
+    def reserve(self, factor=2.0):
+        """Make every list at least ``factor`` x the largest length seen so far (re-captures if something grows).
+        Call it after a few warm-up steps, outside any region whose timing matters."""
+        self.flush()
+        seen = getattr(self, "_seen", None)
+        if seen is None:
+            return self.capacities()
+        caps = self.capacities()
+        want = tuple(max(c, int(factor * v) + 64) for c, v in zip(caps, seen[:3]))
+        self._set_caps(*want)
+        if self.capacities() != caps:
+            new = self.capacities()
+            self._set_caps(*caps)
+            self._recapture(new)
+        return self.capacities()
 
     def flush(self):
         """Settle every step still in flight (end of training / before reading results that must be exact)."""
