@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define TIR_ABI_VERSION 1
+#define TIR_ABI_VERSION 2
 
 typedef enum TirStatus {
   TIR_OK = 0,
@@ -298,6 +298,86 @@ int tir_epilogue_fwd(int64_t n, const float* packed, const float* acc, const flo
 int tir_epilogue_bwd(int64_t n, const float* packed, const float* acc, const float* depth, const float* rays,
                      float fresnel0, int32_t bg, const TirRayMaps* g_out, const float* g_loss_albedo,
                      const float* g_loss_rough, float* g_packed, float* g_acc, float* g_depth, void* stream);
+
+/* ---- fused primary march: TensorBase.forward (models/tensorBase_rotated_lights.py:868-1036) with is_relight=True as
+ * three calls that chain every kernel of the path on the caller's stream, without host synchronisation:
+ *   tir_primary_march     sample_ray + aabb / alpha-mask filter -> ray-sorted valid list -> compute_densityfeature ->
+ *                         feature2density -> raw2alpha / acc / depth -> per-ray counts of the appearance samples
+ *   tir_primary_heads     appearance list (weight > rayMarch_weight_thres) -> the appearance heads (radiance, BRDF,
+ *                         BRDF at jittered points, predicted normal) -> derived normals -> per-sample costs and the 14
+ *                         composited channels -> per-ray epilogue (background, clamps, sRGB, normalise, acc_mask)
+ *   tir_primary_backward  the whole backward of both, gradients ACCUMULATED into caller-zeroed buffers
+ * All lists live in caller-allocated scratch of static capacity; their real lengths stay on the device
+ * (work->offsets[n_rays], work->a_offsets[n_rays]); rows that do not fit are dropped and flagged in work->status, so the
+ * caller can size the lists exactly (count pass + host read between the calls) or statically (CUDA-graph capture). */
+#define TIR_MAX_HEADS 4
+
+typedef struct TirHeadJob {
+  TirMlp mlp;                 /* light_line = the full [n_lights,3*aC] table (or NULL) */
+  int32_t point_set;          /* 0: appearance samples, 1: the same samples jittered by 0.01*N(0,1) (tensorBase:937) */
+  int32_t x_in;               /* 0: view direction of the sample's ray, 1: the (normalised) sample point itself */
+  int32_t light_mode;         /* 0 none, 1 light_line[light_idx[ray]], 2 mean over the lights (compute_intrinfeature) */
+  int32_t act;                /* 0 sigmoid, 1 tanh */
+  int32_t role;               /* TIR_HEAD_RGB / _BRDF / _BRDF_JITTER / _NORMAL */
+} TirHeadJob;
+enum { TIR_HEAD_RGB = 0, TIR_HEAD_BRDF = 1, TIR_HEAD_BRDF_JITTER = 2, TIR_HEAD_NORMAL = 3 };
+enum { TIR_NORMALS_DERIVED_PLUS_PREDICTED = 0, TIR_NORMALS_PREDICTED = 1, TIR_NORMALS_DERIVED = 2 };
+
+typedef struct TirPrimaryWork {
+  int64_t cap_valid, cap_app;
+  /* per ray */
+  int32_t* counts;            /* [n_rays] valid samples */
+  int64_t* offsets;           /* [n_rays+1] exclusive scan; offsets[n_rays] = real length of the valid list */
+  float* t_last; float* acc; float* depth;          /* [n_rays] */
+  int32_t* a_counts; int64_t* a_offsets;            /* appearance samples per ray, scan */
+  float* packed;              /* [n_rays,14] composited channels */
+  /* valid list [cap_valid] */
+  int32_t* v_ray; int32_t* v_sample; float* v_xn; float* v_z; float* v_dist;
+  float* v_feat; float* v_sigma; float* v_weight; float* v_trans;
+  /* appearance list [cap_app] */
+  int64_t* a_src;             /* row of the valid list */
+  int32_t* a_ray; float* a_w; float* a_xn; float* a_xj;
+  const float* noise;         /* [cap_app,3] N(0,1) draws for the jittered points */
+  float* x0[2];               /* raw plane*line products per point set [cap_app,3*aC] (NULL: not saved, no backward) */
+  float* inp[TIR_MAX_HEADS]; float* h1[TIR_MAX_HEADS]; float* h2[TIR_MAX_HEADS];   /* activation dumps (or NULL) */
+  float* out[TIR_MAX_HEADS];  /* [cap_app,4] head outputs */
+  float* dn_feat; float* dn_dfdx;                   /* derived-normal inputs [cap_app], [cap_app,3] */
+  int64_t* status;            /* [4]: real valid count, real appearance count, overflow flag (0/1), reserved */
+} TirPrimaryWork;
+
+typedef struct TirPrimaryBwdWork {
+  float* g_packed; float* g_acc; float* g_depth;    /* [n_rays,14], [n_rays], [n_rays] */
+  float* g_weight; float* g_feat;                   /* [cap_valid] */
+  float* g_out[TIR_MAX_HEADS];                      /* [cap_app,4] */
+  float* gz1[TIR_MAX_HEADS]; float* gz2[TIR_MAX_HEADS];   /* [cap_app,hidden] */
+  float* gfeat[TIR_MAX_HEADS];                      /* [cap_app,32] */
+  float* gx0[TIR_MAX_HEADS];                        /* [cap_app,3*aC] */
+  float* g_dn_feat; float* g_dn_dfdx;               /* [cap_app], [cap_app,3] */
+} TirPrimaryBwdWork;
+
+typedef struct TirPrimaryGrads {      /* accumulated (+=); the caller zeroes them (they may be the .grad tensors) */
+  float* dplane[3]; float* dline[3]; float* aplane[3]; float* aline[3];   /* channel-last, like TirField */
+  float* basis; float* light_line;
+  float* w0[TIR_MAX_HEADS]; float* b0[TIR_MAX_HEADS]; float* w1[TIR_MAX_HEADS]; float* b1[TIR_MAX_HEADS];
+  float* w2[TIR_MAX_HEADS]; float* b2[TIR_MAX_HEADS];   /* per job; jobs of the same module share buffers */
+} TirPrimaryGrads;
+
+int tir_primary_march(const TirField* field, const float* rays /* [n_rays,6] origin | direction */, int64_t n_rays,
+                      const TirMarchCfg* cfg, const TirPrimaryWork* work, uint64_t* counters, void* stream);
+/* appearance list of the march (rows of the valid list with weight > rayMarch_weight_thres, in list order): fills
+ * work->a_src / a_ray / a_w / a_xn; its real length is work->a_offsets[n_rays].  Separate so that the caller can draw the
+ * jitter noise (work->noise) for exactly these rows before tir_primary_heads. */
+int tir_primary_app_list(const TirField* field, int64_t n_rays, const TirPrimaryWork* work, void* stream);
+int tir_primary_heads(const TirField* field, const TirHeadJob* jobs, int32_t n_jobs, int32_t normals_kind,
+                      const float* rays, const int32_t* light_idx /* [n_rays] */, int64_t n_rays,
+                      const TirPrimaryWork* work, float fresnel0, int32_t white_bg, const TirRayMaps* out,
+                      uint8_t* acc_mask, float* losses /* [2] */, uint64_t* counters, void* stream);
+int tir_primary_backward(const TirField* field, const TirHeadJob* jobs, int32_t n_jobs, int32_t normals_kind,
+                         const float* rays, const int32_t* light_idx, int64_t n_rays, const TirPrimaryWork* work,
+                         const TirPrimaryBwdWork* bwork, float fresnel0, int32_t white_bg,
+                         const TirRayMaps* g_maps /* gradients of the maps, members may be NULL */,
+                         const float* g_acc_map /* [n_rays] or NULL */, const float* g_loss_albedo,
+                         const float* g_loss_rough, const TirPrimaryGrads* grads, void* stream);
 
 #ifdef __cplusplus
 }

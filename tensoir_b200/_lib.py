@@ -14,7 +14,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TIR_LIB") or os.path.join(_HERE, "lib", "libtensoir_b200.so")   # TIR_LIB: A/B builds
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 CNT_MASK, CNT_DENSITY, CNT_APP, CNT_RAYS, CNT_OVERFLOW, CNT_SLOTS = 0, 1, 2, 3, 4, 8
 SAMPLE_STEP, SAMPLE_TABLE = 0, 1
 
@@ -58,6 +58,39 @@ class TirRayMaps(C.Structure):
 
 
 APP_SAMPLE_BYTES = 24  # sizeof(TirAppSample)
+MAX_HEADS = 4          # TIR_MAX_HEADS
+
+
+# ---- fused primary march (csrc/tir_primary.cu) ------------------------------------------------------------------------
+class TirHeadJob(C.Structure):
+    _fields_ = [("mlp", TirMlp), ("point_set", C.c_int32), ("x_in", C.c_int32), ("light_mode", C.c_int32),
+                ("act", C.c_int32), ("role", C.c_int32)]
+
+
+class TirPrimaryWork(C.Structure):
+    _fields_ = ([("cap_valid", C.c_int64), ("cap_app", C.c_int64)]
+                + [(k, C.c_void_p) for k in ("counts", "offsets", "t_last", "acc", "depth", "a_counts", "a_offsets",
+                                             "packed", "v_ray", "v_sample", "v_xn", "v_z", "v_dist", "v_feat",
+                                             "v_sigma", "v_weight", "v_trans", "a_src", "a_ray", "a_w", "a_xn", "a_xj",
+                                             "noise")]
+                + [("x0", C.c_void_p * 2), ("inp", C.c_void_p * MAX_HEADS), ("h1", C.c_void_p * MAX_HEADS),
+                   ("h2", C.c_void_p * MAX_HEADS), ("out", C.c_void_p * MAX_HEADS), ("dn_feat", C.c_void_p),
+                   ("dn_dfdx", C.c_void_p), ("status", C.c_void_p)])
+
+
+class TirPrimaryBwdWork(C.Structure):
+    _fields_ = ([(k, C.c_void_p) for k in ("g_packed", "g_acc", "g_depth", "g_weight", "g_feat")]
+                + [("g_out", C.c_void_p * MAX_HEADS), ("gz1", C.c_void_p * MAX_HEADS), ("gz2", C.c_void_p * MAX_HEADS),
+                   ("gfeat", C.c_void_p * MAX_HEADS), ("gx0", C.c_void_p * MAX_HEADS), ("g_dn_feat", C.c_void_p),
+                   ("g_dn_dfdx", C.c_void_p)])
+
+
+class TirPrimaryGrads(C.Structure):
+    _fields_ = ([("dplane", C.c_void_p * 3), ("dline", C.c_void_p * 3), ("aplane", C.c_void_p * 3),
+                 ("aline", C.c_void_p * 3), ("basis", C.c_void_p), ("light_line", C.c_void_p)]
+                + [(k, C.c_void_p * MAX_HEADS) for k in ("w0", "b0", "w1", "b1", "w2", "b2")])
+
+
 
 EXPORTS = {
     "tir_abi_version": (C.c_int, []),
@@ -103,6 +136,16 @@ EXPORTS = {
                                     f32p, f32p, f32p, C.c_void_p]),
     "tir_composite_bwd": (C.c_int, [f32p, f32p, C.c_void_p, C.c_int64, C.c_float, f32p, f32p, f32p, f32p,
                                     C.c_int64, f32p, f32p, f32p, C.c_void_p]),
+    "tir_primary_march": (C.c_int, [C.POINTER(TirField), C.c_void_p, C.c_int64, C.POINTER(TirMarchCfg),
+                                    C.POINTER(TirPrimaryWork), C.c_void_p, C.c_void_p]),
+    "tir_primary_app_list": (C.c_int, [C.POINTER(TirField), C.c_int64, C.POINTER(TirPrimaryWork), C.c_void_p]),
+    "tir_primary_heads": (C.c_int, [C.POINTER(TirField), C.POINTER(TirHeadJob), C.c_int32, C.c_int32, C.c_void_p,
+                                    C.c_void_p, C.c_int64, C.POINTER(TirPrimaryWork), C.c_float, C.c_int32,
+                                    C.POINTER(TirRayMaps), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tir_primary_backward": (C.c_int, [C.POINTER(TirField), C.POINTER(TirHeadJob), C.c_int32, C.c_int32, C.c_void_p,
+                                       C.c_void_p, C.c_int64, C.POINTER(TirPrimaryWork), C.POINTER(TirPrimaryBwdWork),
+                                       C.c_float, C.c_int32, C.POINTER(TirRayMaps), C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.POINTER(TirPrimaryGrads), C.c_void_p]),
     "tir_tail_fwd": (C.c_int, [C.c_int64, f32p, C.c_void_p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, C.c_void_p]),
     "tir_tail_bwd": (C.c_int, [C.c_int64, f32p, C.c_void_p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p,
                                f32p, f32p, f32p, C.c_void_p]),
@@ -119,6 +162,8 @@ KERNELS_PER_CALL = {"tir_pack_channels_last": 1, "tir_unpack_channels_last_add":
                     "tir_shade_fwd": 1, "tir_shade_bwd": 1, "tir_app_mlp_points": 1, "tir_app_mlp_points_save": 1, "tir_vm_app_products": 1, "tir_vm_app_products_bwd": 1,
                     "tir_vm_density_bwd": 1, "tir_vm_density_grad": 1, "tir_vm_density_grad_bwd": 1,
                     "tir_valid_samples_count": 1, "tir_valid_samples_fill": 1, "tir_composite_fwd": 1,
+                    "tir_primary_march": 6, "tir_primary_app_list": 1, "tir_primary_heads": 5,
+                    "tir_primary_backward": 9,
                     "tir_composite_bwd": 1, "tir_tail_fwd": 1, "tir_tail_bwd": 1, "tir_epilogue_fwd": 1,
                     "tir_epilogue_bwd": 1}
 launch_count = 0

@@ -11,6 +11,7 @@
 // buffer; fragments are fetched with ldmatrix from rows padded to an odd multiple of 16 bytes (conflict free).
 #include <cuda_bf16.h>
 #include "tir_device.cuh"
+#include "tir_internal.h"
 
 using namespace tir;
 
@@ -39,6 +40,7 @@ struct Smem {
   __nv_bfloat16 w2h[ON * SW2], w2l[ON * SW2];
   __nv_bfloat16 ah[M * SA], al[M * SA];      // activations, in place across layers
   float b0[HID], b1[HID], b2[ON];
+  float lmean[K0];                           // mean light row (light_mode 2, compute_intrinfeature)
   float xn[M][3];
   float xv[M][3];
   float wgt[M];
@@ -56,17 +58,13 @@ struct MlpParams {
   int n_dirs;
   const int32_t* light_idx;
   float* rgb_out;
-  const float* pts_xn;
-  const float* pts_x;
+  // POINTS mode: up to 4 heads, CTA b works on job b % n_jobs (tir_internal.h)
+  HeadJobDev jobs[kMaxHeadJobs];
+  int n_jobs;
   int64_t n_points;
-  float* out;
-  int act;        // 0 sigmoid, 1 tanh
-  // optional activation dumps for a host-side backward (training): [n,144] light-scaled products, [n,150] MLP input,
-  // [n,128] hidden 1 / 2 (post-ReLU)
+  const int64_t* n_dev;   // optional device-side row count (<= n_points)
+  // legacy dump of the light-scaled products [n,144] (modular heads.py backward); job 0 only
   float* save_xl;
-  float* save_in;
-  float* save_h1;
-  float* save_h2;
 };
 
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& h, __nv_bfloat16& l) {
@@ -166,8 +164,13 @@ __global__ void __launch_bounds__(NT, 1) app_mlp_kernel(const MlpParams p) {
   Smem& s = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t4 = lane & 3;
-  const TirMlp& mlp = p.mlp;
+  const int n_jobs = POINTS ? p.n_jobs : 1;
+  const int job = POINTS ? (int)(blockIdx.x % n_jobs) : 0;
+  const HeadJobDev& J = p.jobs[job];
+  const TirMlp& mlp = POINTS ? J.mlp : p.mlp;
   const int out_dim = mlp.out_dim;
+  const int light_mode = POINTS ? J.light_mode : (mlp.light_line ? 1 : 0);
+  const int act = POINTS ? J.act : 0;
 
   // ---- stage split-BF16 weights once per CTA (PyTorch [out,in] layout is already the mma "col" operand)
   for (int i = tid; i < HID * SW0; i += NT) {
@@ -188,13 +191,22 @@ __global__ void __launch_bounds__(NT, 1) app_mlp_kernel(const MlpParams p) {
   }
   for (int i = tid; i < HID; i += NT) { s.b0[i] = __ldg(mlp.b0 + i); s.b1[i] = __ldg(mlp.b1 + i); }
   if (tid < ON) s.b2[tid] = (tid < out_dim) ? __ldg(mlp.b2 + tid) : 0.f;
+  if (light_mode == 2) {   // torch.mean(light_line(arange(L)), 0)  (tensoRF_rotated_lights.py:160-161)
+    for (int c = tid; c < K0; c += NT) {
+      float a = 0.f;
+      for (int l = 0; l < mlp.n_lights; ++l) a += __ldg(mlp.light_line + (size_t)l * K0 + c);
+      s.lmean[c] = a / (float)mlp.n_lights;
+    }
+  }
   __syncthreads();
 
-  const int64_t total = POINTS ? p.n_points
+  const int64_t total = POINTS ? list_rows(p.n_points, p.n_dev)
                                : (int64_t)min((unsigned long long)*p.sample_count, (unsigned long long)p.max_samples);
   const int64_t n_tiles = (total + M - 1) / M;
+  const int64_t tile0 = POINTS ? (int64_t)(blockIdx.x / n_jobs) : (int64_t)blockIdx.x;
+  const int64_t tstep = POINTS ? (int64_t)(gridDim.x / n_jobs) : (int64_t)gridDim.x;
 
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  for (int64_t tile = tile0; tile < n_tiles; tile += tstep) {
     const int64_t base = tile * M;
     // ---- sample metadata
     if (tid < M) {
@@ -203,10 +215,12 @@ __global__ void __launch_bounds__(NT, 1) app_mlp_kernel(const MlpParams p) {
       int ray = -1, li = 0;
       if (i < total) {
         if (POINTS) {
-          xn0 = p.pts_xn[i * 3 + 0]; xn1 = p.pts_xn[i * 3 + 1]; xn2 = p.pts_xn[i * 3 + 2];
-          v0 = p.pts_x[i * 3 + 0]; v1 = p.pts_x[i * 3 + 1]; v2 = p.pts_x[i * 3 + 2];
+          xn0 = J.xn[i * 3 + 0]; xn1 = J.xn[i * 3 + 1]; xn2 = J.xn[i * 3 + 2];
+          const int64_t r = J.x_index ? (int64_t)J.x_index[i] : i;
+          const float* xi = J.x_in + r * J.x_in_stride;
+          v0 = xi[0]; v1 = xi[1]; v2 = xi[2];
           ray = (int)i; w = 1.f;
-          li = p.light_idx ? p.light_idx[i] : 0;
+          li = J.light_idx ? J.light_idx[r] : 0;
         } else {
           const TirAppSample sm = p.samples[i];
           xn0 = sm.xn[0]; xn1 = sm.xn[1]; xn2 = sm.xn[2]; w = sm.weight; ray = sm.ray;
@@ -225,7 +239,9 @@ __global__ void __launch_bounds__(NT, 1) app_mlp_kernel(const MlpParams p) {
     {
       const int m = tid >> 2, qd = tid & 3;
       const float xn[3] = {s.xn[m][0], s.xn[m][1], s.xn[m][2]};
-      const float* lrow = mlp.light_line ? (mlp.light_line + (size_t)s.light[m] * K0) : nullptr;
+      const float* lrow = light_mode == 1 ? (mlp.light_line + (size_t)s.light[m] * K0)
+                                          : (light_mode == 2 ? s.lmean : nullptr);
+      float* x0_dst = (POINTS && J.save_x0 && base + m < total) ? J.save_x0 + (base + m) * K0 : nullptr;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         const int m0 = kMat0[k], m1 = kMat1[k], v = kVec[k];
@@ -241,8 +257,9 @@ __global__ void __launch_bounds__(NT, 1) app_mlp_kernel(const MlpParams p) {
           const float4 lv = lerp4(ldg4(L + (size_t)l.o0 * AC + c), ldg4(L + (size_t)l.o1 * AC + c), l);
           float4 x = make_float4(__fmul_rn(pv.x, lv.x), __fmul_rn(pv.y, lv.y), __fmul_rn(pv.z, lv.z),
                                  __fmul_rn(pv.w, lv.w));
+          if (x0_dst) *reinterpret_cast<float4*>(x0_dst + k * AC + c) = x;   // raw products for the backward
           if (lrow) {   // (plane * line) * light  (tensoRF_rotated_lights.py:222)
-            const float4 lc = ldg4(lrow + k * AC + c);
+            const float4 lc = *reinterpret_cast<const float4*>(lrow + k * AC + c);
             x.x = __fmul_rn(x.x, lc.x); x.y = __fmul_rn(x.y, lc.y); x.z = __fmul_rn(x.z, lc.z); x.w = __fmul_rn(x.w, lc.w);
           }
           const int col = k * AC + c;
@@ -252,7 +269,7 @@ __global__ void __launch_bounds__(NT, 1) app_mlp_kernel(const MlpParams p) {
       }
     }
     __syncthreads();
-    if (POINTS && p.save_xl) dump_tile(s.ah, s.al, p.save_xl, K0, base, total, tid);
+    if (POINTS && p.save_xl && job == 0) dump_tile(s.ah, s.al, p.save_xl, K0, base, total, tid);
 
     // ---- phase 2: basis_mat (144 -> 27, N padded to 32): warp w -> m-tile w/2, n-tiles 2*(w%2), +1
     {
@@ -303,7 +320,7 @@ __global__ void __launch_bounds__(NT, 1) app_mlp_kernel(const MlpParams p) {
       }
     }
     __syncthreads();
-    if (POINTS && p.save_in) dump_tile(s.ah, s.al, p.save_in, IN, base, total, tid);
+    if (POINTS && J.save_in) dump_tile(s.ah, s.al, J.save_in, IN, base, total, tid);
 
     // ---- phases 3/4: hidden layers.  warp w -> all 64 rows x units [16w, 16w+16)
     auto hidden_layer = [&](const __nv_bfloat16* wh, const __nv_bfloat16* wl, int sw, const float* bias, int K) {
@@ -323,9 +340,9 @@ __global__ void __launch_bounds__(NT, 1) app_mlp_kernel(const MlpParams p) {
       __syncthreads();
     };
     hidden_layer(s.w0h, s.w0l, SW0, s.b0, K1);
-    if (POINTS && p.save_h1) dump_tile(s.ah, s.al, p.save_h1, HID, base, total, tid);
+    if (POINTS && J.save_h1) dump_tile(s.ah, s.al, J.save_h1, HID, base, total, tid);
     hidden_layer(s.w1h, s.w1l, SW1, s.b1, HID);
-    if (POINTS && p.save_h2) dump_tile(s.ah, s.al, p.save_h2, HID, base, total, tid);
+    if (POINTS && J.save_h2) dump_tile(s.ah, s.al, J.save_h2, HID, base, total, tid);
 
     // ---- phase 5: output layer (N padded to 8) on warps 0..3, activation, composite
     if (warp < 4) {
@@ -337,10 +354,10 @@ __global__ void __launch_bounds__(NT, 1) app_mlp_kernel(const MlpParams p) {
         const int o = 2 * t4 + (e & 1);
         if (o < out_dim) {
           const float a = acc[0][0][e] + s.b2[o];
-          const float y = p.act == 0 ? 1.f / (1.f + expf(-a)) : tanhf(a);
+          const float y = act == 0 ? 1.f / (1.f + expf(-a)) : tanhf(a);
           const int64_t i = base + row;
           if (i < total) {
-            if (POINTS) p.out[i * out_dim + o] = y;
+            if (POINTS) J.out[i * J.out_stride + o] = y;
             else atomicAdd(p.rgb_out + (int64_t)s.ray[row] * 3 + o, __fmul_rn(s.wgt[row], y));
           }
         }
@@ -368,8 +385,10 @@ int launch(const MlpParams& p, int64_t max_items, cudaStream_t stream) {
     configured[POINTS] = true;
   }
   int64_t tiles = (max_items + M - 1) / M;
-  int blocks = (int)(tiles < 148 ? (tiles > 0 ? tiles : 1) : 148);
-  app_mlp_kernel<POINTS><<<blocks, NT, smem, stream>>>(p);
+  const int nj = POINTS ? (p.n_jobs > 0 ? p.n_jobs : 1) : 1;
+  int per_job = 148 / nj;                              // CTAs per job: one wave, one CTA per SM
+  if (tiles < per_job) per_job = (int)(tiles > 0 ? tiles : 1);
+  app_mlp_kernel<POINTS><<<per_job * nj, NT, smem, stream>>>(p);
   return (int)cudaGetLastError();
 }
 
@@ -384,8 +403,17 @@ extern "C" int tir_app_mlp(const TirField* field, const TirMlp* mlp, const TirAp
   if (mlp->out_dim != 3) return TIR_ERR_SHAPE;
   MlpParams p{};
   p.f = *field; p.mlp = *mlp; p.samples = samples; p.sample_count = sample_count; p.max_samples = max_samples;
-  p.ray_dirs = ray_dirs; p.n_dirs = n_dirs; p.light_idx = light_idx; p.rgb_out = rgb_out; p.act = 0;
+  p.ray_dirs = ray_dirs; p.n_dirs = n_dirs; p.light_idx = light_idx; p.rgb_out = rgb_out;
   return launch<false>(p, max_samples, (cudaStream_t)stream);
+}
+
+static void legacy_job(MlpParams& p, const TirMlp* mlp, const float* xn, const float* x_in, const int32_t* light_idx,
+                       int64_t n, int32_t act, float* out) {
+  p.n_jobs = 1; p.n_points = n; p.n_dev = nullptr;
+  HeadJobDev& J = p.jobs[0];
+  J = HeadJobDev{};
+  J.mlp = *mlp; J.xn = xn; J.x_in = x_in; J.x_index = nullptr; J.x_in_stride = 3; J.light_idx = light_idx;
+  J.light_mode = mlp->light_line ? 1 : 0; J.act = act; J.out = out; J.out_stride = mlp->out_dim;
 }
 
 extern "C" int tir_app_mlp_points_save(const TirField* field, const TirMlp* mlp, const float* xn, const float* x_in,
@@ -397,9 +425,9 @@ extern "C" int tir_app_mlp_points_save(const TirField* field, const TirMlp* mlp,
   if (rc) return rc;
   if (act != 0 && act != 1) return TIR_ERR_CONFIG;
   MlpParams p{};
-  p.f = *field; p.mlp = *mlp; p.pts_xn = xn; p.pts_x = x_in; p.n_points = n; p.light_idx = light_idx;
-  p.out = out; p.act = act;
-  p.save_xl = save_xl; p.save_in = save_in; p.save_h1 = save_h1; p.save_h2 = save_h2;
+  p.f = *field;
+  legacy_job(p, mlp, xn, x_in, light_idx, n, act, out);
+  p.save_xl = save_xl; p.jobs[0].save_in = save_in; p.jobs[0].save_h1 = save_h1; p.jobs[0].save_h2 = save_h2;
   return launch<true>(p, n, (cudaStream_t)stream);
 }
 
@@ -411,7 +439,25 @@ extern "C" int tir_app_mlp_points(const TirField* field, const TirMlp* mlp, cons
   if (rc) return rc;
   if (act != 0 && act != 1) return TIR_ERR_CONFIG;
   MlpParams p{};
-  p.f = *field; p.mlp = *mlp; p.pts_xn = xn; p.pts_x = x_in; p.n_points = n; p.light_idx = light_idx;
-  p.out = out; p.act = act;
+  p.f = *field;
+  legacy_job(p, mlp, xn, x_in, light_idx, n, act, out);
   return launch<true>(p, n, (cudaStream_t)stream);
 }
+
+namespace tir {
+int launch_heads_forward(const TirField& f, const HeadJobDev* jobs, int n_jobs, int64_t n, const int64_t* n_dev,
+                         cudaStream_t stream) {
+  if (n <= 0 || n_jobs <= 0) return TIR_OK;
+  if (n_jobs > kMaxHeadJobs) return TIR_ERR_CONFIG;
+  MlpParams p{};
+  p.f = f; p.n_jobs = n_jobs; p.n_points = n; p.n_dev = n_dev;
+  for (int j = 0; j < n_jobs; ++j) {
+    int rc = check_shapes(&f, &jobs[j].mlp);
+    if (rc) return rc;
+    if (!jobs[j].xn || !jobs[j].x_in || !jobs[j].out) return TIR_ERR_NULL;
+    if (jobs[j].light_mode != 0 && !jobs[j].mlp.light_line) return TIR_ERR_NULL;
+    p.jobs[j] = jobs[j];
+  }
+  return launch<true>(p, n, stream);
+}
+}  // namespace tir

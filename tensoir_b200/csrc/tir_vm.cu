@@ -6,6 +6,7 @@
 //   * ray-sorted valid-sample lists (count / fill) and the sequential compositing scan with its backward
 //     (raw2alpha, tensorBase:21-28)
 #include "tir_device.cuh"
+#include "tir_internal.h"
 
 using namespace tir;
 
@@ -95,14 +96,11 @@ __global__ void app_products_kernel(TirField f, const float* __restrict__ xn, in
   }
 }
 
-struct GradPtrs {
-  float* plane[3];
-  float* line[3];
-};
-
 template <int C>
-__global__ void app_products_bwd_kernel(TirField f, const float* __restrict__ xn, int64_t n,
-                                        const float* __restrict__ gout, GradPtrs g) {
+__global__ void app_products_bwd_kernel(TirField f, const float* __restrict__ xn, int64_t n_cap,
+                                        const int64_t* __restrict__ n_dev, const float* __restrict__ gout,
+                                        const float* __restrict__ gout1, const float* __restrict__ gout2, GradPtrs g) {
+  const int64_t n = list_rows(n_cap, n_dev);
   const int64_t total = n * 3;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = t / 3;
@@ -113,9 +111,11 @@ __global__ void app_products_bwd_kernel(TirField f, const float* __restrict__ xn
     const Linear1 l = linear_setup(x[v], f.grid[v]);
     const float* P = f.aplane[k];
     const float* L = f.aline[k];
-    const float* go = gout + i * (3 * C) + k * C;
+    const int64_t go_off = i * (3 * C) + k * C;
     for (int c = 0; c < C; c += 4) {
-      const float4 gv = *reinterpret_cast<const float4*>(go + c);
+      float4 gv = *reinterpret_cast<const float4*>(gout + go_off + c);
+      if (gout1) gv = f4_add(gv, *reinterpret_cast<const float4*>(gout1 + go_off + c));   // heads sharing the points
+      if (gout2) gv = f4_add(gv, *reinterpret_cast<const float4*>(gout2 + go_off + c));
       const float4 pv = bilerp4(ldg4(P + (size_t)b.o00 * C + c), ldg4(P + (size_t)b.o01 * C + c),
                                 ldg4(P + (size_t)b.o10 * C + c), ldg4(P + (size_t)b.o11 * C + c), b);
       const float4 lv = lerp4(ldg4(L + (size_t)l.o0 * C + c), ldg4(L + (size_t)l.o1 * C + c), l);
@@ -133,9 +133,9 @@ __global__ void app_products_bwd_kernel(TirField f, const float* __restrict__ xn
 
 // density feature backward (zero-padding sampler): d L / d feature[i] = gout[i]
 template <int C>
-__global__ void density_bwd_kernel(TirField f, const float* __restrict__ xn, int64_t n,
-                                   const float* __restrict__ gout, GradPtrs g) {
-  const int64_t total = n * 3;
+__global__ void density_bwd_kernel(TirField f, const float* __restrict__ xn, int64_t n_cap,
+                                   const int64_t* __restrict__ n_dev, const float* __restrict__ gout, GradPtrs g) {
+  const int64_t total = list_rows(n_cap, n_dev) * 3;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = t / 3;
     const int k = (int)(t - i * 3);
@@ -168,8 +168,10 @@ __global__ void density_bwd_kernel(TirField f, const float* __restrict__ xn, int
 // density feature + spatial gradient (clamped sampler), forward / backward
 // ------------------------------------------------------------------------------------------------------------------
 template <int C>
-__global__ void density_grad_kernel(TirField f, const float* __restrict__ xn, int64_t n, float* __restrict__ feat,
+__global__ void density_grad_kernel(TirField f, const float* __restrict__ xn, int64_t n_cap,
+                                    const int64_t* __restrict__ n_dev, float* __restrict__ feat,
                                     float* __restrict__ dfdx) {
+  const int64_t n = list_rows(n_cap, n_dev);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float x[3] = {xn[i * 3], xn[i * 3 + 1], xn[i * 3 + 2]};
     float ft = 0.f, gr[3] = {0.f, 0.f, 0.f};
@@ -208,10 +210,10 @@ __global__ void density_grad_kernel(TirField f, const float* __restrict__ xn, in
 }
 
 template <int C>
-__global__ void density_grad_bwd_kernel(TirField f, const float* __restrict__ xn, int64_t n,
-                                        const float* __restrict__ g_feat, const float* __restrict__ g_dfdx,
-                                        GradPtrs g) {
-  const int64_t total = n * 3;
+__global__ void density_grad_bwd_kernel(TirField f, const float* __restrict__ xn, int64_t n_cap,
+                                        const int64_t* __restrict__ n_dev, const float* __restrict__ g_feat,
+                                        const float* __restrict__ g_dfdx, GradPtrs g) {
+  const int64_t total = list_rows(n_cap, n_dev) * 3;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = t / 3;
     const int k = (int)(t - i * 3);
@@ -261,12 +263,12 @@ __global__ void valid_samples_kernel(TirField f, TirMarchCfg cfg, const float* _
                                      const int64_t* __restrict__ offsets, int32_t* __restrict__ out_ray,
                                      int32_t* __restrict__ out_sample, float* __restrict__ out_xn,
                                      float* __restrict__ out_z, float* __restrict__ out_dist,
-                                     unsigned long long* counters, int64_t capacity) {
+                                     unsigned long long* counters, int64_t capacity, int stride) {
   const int lane = threadIdx.x & 31;
   const int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (ray >= n_rays) return;
-  const float ox = rays_o[ray * 3], oy = rays_o[ray * 3 + 1], oz = rays_o[ray * 3 + 2];
-  const float dx = rays_d[ray * 3], dy = rays_d[ray * 3 + 1], dz = rays_d[ray * 3 + 2];
+  const float ox = rays_o[ray * stride], oy = rays_o[ray * stride + 1], oz = rays_o[ray * stride + 2];
+  const float dx = rays_d[ray * stride], dy = rays_d[ray * stride + 1], dz = rays_d[ray * stride + 2];
   const int N = cfg.n_samples;
   float tmin = 0.f, jit = 0.f;
   if (cfg.sampling == TIR_SAMPLE_STEP) {
@@ -379,6 +381,52 @@ inline int blocks_for(int64_t n, int threads, int cap = 148 * 16) {
 
 }  // namespace
 
+namespace tir {
+int launch_valid_samples(const TirField& f, const TirMarchCfg& cfg, const float* rays, int64_t n_rays, bool fill,
+                         int32_t* counts, const int64_t* offsets, int32_t* out_ray, int32_t* out_sample, float* out_xn,
+                         float* out_z, float* out_dist, uint64_t* counters, int64_t capacity, cudaStream_t stream) {
+  if (n_rays <= 0) return TIR_OK;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((n_rays * 32 + threads - 1) / threads);
+  if (fill)
+    valid_samples_kernel<true><<<blocks, threads, 0, stream>>>(f, cfg, rays, rays + 3, n_rays, nullptr, offsets, out_ray,
+                                                               out_sample, out_xn, out_z, out_dist, nullptr, capacity, 6);
+  else
+    valid_samples_kernel<false><<<blocks, threads, 0, stream>>>(f, cfg, rays, rays + 3, n_rays, counts, nullptr, nullptr,
+                                                                nullptr, nullptr, nullptr, nullptr,
+                                                                (unsigned long long*)counters, 0, 6);
+  return (int)cudaGetLastError();
+}
+int launch_density_bwd(const TirField& f, const float* xn, int64_t n, const int64_t* n_dev, const float* g_feature,
+                       const GradPtrs& g, cudaStream_t stream) {
+  if (n <= 0) return TIR_OK;
+  if (f.dC != 16) return TIR_ERR_SHAPE;
+  density_bwd_kernel<16><<<blocks_for(n * 3, 128), 128, 0, stream>>>(f, xn, n, n_dev, g_feature, g);
+  return (int)cudaGetLastError();
+}
+int launch_app_products_bwd(const TirField& f, const float* xn, int64_t n, const int64_t* n_dev, const float* g0,
+                            const float* g1, const float* g2, const GradPtrs& g, cudaStream_t stream) {
+  if (n <= 0) return TIR_OK;
+  if (f.aC != 48) return TIR_ERR_SHAPE;
+  app_products_bwd_kernel<48><<<blocks_for(n * 3, 128), 128, 0, stream>>>(f, xn, n, n_dev, g0, g1, g2, g);
+  return (int)cudaGetLastError();
+}
+int launch_density_grad(const TirField& f, const float* xn, int64_t n, const int64_t* n_dev, float* feature,
+                        float* dfdx, cudaStream_t stream) {
+  if (n <= 0) return TIR_OK;
+  if (f.dC != 16) return TIR_ERR_SHAPE;
+  density_grad_kernel<16><<<blocks_for(n, 128), 128, 0, stream>>>(f, xn, n, n_dev, feature, dfdx);
+  return (int)cudaGetLastError();
+}
+int launch_density_grad_bwd(const TirField& f, const float* xn, int64_t n, const int64_t* n_dev, const float* g_feature,
+                            const float* g_dfdx, const GradPtrs& g, cudaStream_t stream) {
+  if (n <= 0) return TIR_OK;
+  if (f.dC != 16) return TIR_ERR_SHAPE;
+  density_grad_bwd_kernel<16><<<blocks_for(n * 3, 128), 128, 0, stream>>>(f, xn, n, n_dev, g_feature, g_dfdx, g);
+  return (int)cudaGetLastError();
+}
+}  // namespace tir
+
 extern "C" int tir_vm_app_products(const TirField* field, const float* xn, int64_t n, float* out, void* stream) {
   if (n <= 0) return TIR_OK;   // empty input: nothing to do (pointers of empty tensors are NULL)
   if (!field || !xn || !out) return TIR_ERR_NULL;
@@ -394,7 +442,8 @@ extern "C" int tir_vm_app_products_bwd(const TirField* field, const float* xn, i
   if (field->aC != 48) return TIR_ERR_SHAPE;
   GradPtrs g;
   for (int k = 0; k < 3; ++k) { g.plane[k] = g_plane[k]; g.line[k] = g_line[k]; }
-  app_products_bwd_kernel<48><<<blocks_for(n * 3, 128), 128, 0, (cudaStream_t)stream>>>(*field, xn, n, g_out, g);
+  app_products_bwd_kernel<48><<<blocks_for(n * 3, 128), 128, 0, (cudaStream_t)stream>>>(*field, xn, n, nullptr, g_out,
+                                                                                       nullptr, nullptr, g);
   return (int)cudaGetLastError();
 }
 
@@ -405,7 +454,7 @@ extern "C" int tir_vm_density_bwd(const TirField* field, const float* xn, int64_
   if (field->dC != 16) return TIR_ERR_SHAPE;
   GradPtrs g;
   for (int k = 0; k < 3; ++k) { g.plane[k] = g_plane[k]; g.line[k] = g_line[k]; }
-  density_bwd_kernel<16><<<blocks_for(n * 3, 128), 128, 0, (cudaStream_t)stream>>>(*field, xn, n, g_feature, g);
+  density_bwd_kernel<16><<<blocks_for(n * 3, 128), 128, 0, (cudaStream_t)stream>>>(*field, xn, n, nullptr, g_feature, g);
   return (int)cudaGetLastError();
 }
 
@@ -414,7 +463,7 @@ extern "C" int tir_vm_density_grad(const TirField* field, const float* xn, int64
   if (n <= 0) return TIR_OK;   // empty input: nothing to do (pointers of empty tensors are NULL)
   if (!field || !xn || !feature || !dfdx) return TIR_ERR_NULL;
   if (field->dC != 16) return TIR_ERR_SHAPE;
-  density_grad_kernel<16><<<blocks_for(n, 128), 128, 0, (cudaStream_t)stream>>>(*field, xn, n, feature, dfdx);
+  density_grad_kernel<16><<<blocks_for(n, 128), 128, 0, (cudaStream_t)stream>>>(*field, xn, n, nullptr, feature, dfdx);
   return (int)cudaGetLastError();
 }
 
@@ -426,8 +475,8 @@ extern "C" int tir_vm_density_grad_bwd(const TirField* field, const float* xn, i
   if (field->dC != 16) return TIR_ERR_SHAPE;
   GradPtrs g;
   for (int k = 0; k < 3; ++k) { g.plane[k] = g_plane[k]; g.line[k] = g_line[k]; }
-  density_grad_bwd_kernel<16><<<blocks_for(n * 3, 128), 128, 0, (cudaStream_t)stream>>>(*field, xn, n, g_feature,
-                                                                                       g_dfdx, g);
+  density_grad_bwd_kernel<16><<<blocks_for(n * 3, 128), 128, 0, (cudaStream_t)stream>>>(*field, xn, n, nullptr,
+                                                                                       g_feature, g_dfdx, g);
   return (int)cudaGetLastError();
 }
 
@@ -442,7 +491,7 @@ extern "C" int tir_valid_samples_count(const TirField* field, const float* rays_
   const int64_t blocks = (n_rays * 32 + threads - 1) / threads;
   valid_samples_kernel<false><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
       *field, *cfg, rays_o, rays_d, n_rays, counts, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-      (unsigned long long*)counters, 0);
+      (unsigned long long*)counters, 0, 3);
   return (int)cudaGetLastError();
 }
 
@@ -458,7 +507,7 @@ extern "C" int tir_valid_samples_fill(const TirField* field, const float* rays_o
   const int64_t blocks = (n_rays * 32 + threads - 1) / threads;
   valid_samples_kernel<true><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
       *field, *cfg, rays_o, rays_d, n_rays, nullptr, offsets, out_ray, out_sample, out_xn, out_z, out_dist, nullptr,
-      capacity > 0 ? capacity : (int64_t)1 << 62);
+      capacity > 0 ? capacity : (int64_t)1 << 62, 3);
   return (int)cudaGetLastError();
 }
 

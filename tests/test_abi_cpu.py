@@ -26,7 +26,7 @@ def test_header_symbols_exported(lib):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
         assert n in _lib.EXPORTS, f"{n} has no ctypes binding"
-    assert lib.tir_abi_version() == 1
+    assert lib.tir_abi_version() == 2
 
 
 def test_struct_sizes_match_header(lib):
@@ -34,6 +34,22 @@ def test_struct_sizes_match_header(lib):
     assert (ctypes.sizeof(_lib.TirField), ctypes.sizeof(_lib.TirMlp), ctypes.sizeof(_lib.TirMarchCfg)) == (224, 88, 48)
     assert _lib.APP_SAMPLE_BYTES == 24
     assert ctypes.sizeof(_lib.TirRayMaps) == 64
+
+
+def test_primary_struct_sizes_match_the_c_compiler(lib, tmp_path):
+    """The ctypes mirrors of the fused-primary structs have the size gcc gives the header's definitions."""
+    import subprocess
+    from tensoir_b200 import _lib
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "tensoir_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu\\n",'
+                   'sizeof(TirHeadJob),sizeof(TirPrimaryWork),sizeof(TirPrimaryBwdWork),sizeof(TirPrimaryGrads),'
+                   'sizeof(TirField),sizeof(TirMlp));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(REPO, "include"), str(src), "-o", str(exe)], check=True)
+    got = tuple(int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split())
+    want = tuple(ctypes.sizeof(t) for t in (_lib.TirHeadJob, _lib.TirPrimaryWork, _lib.TirPrimaryBwdWork,
+                                            _lib.TirPrimaryGrads, _lib.TirField, _lib.TirMlp))
+    assert got == want
 
 
 def test_null_arguments_are_rejected(lib):

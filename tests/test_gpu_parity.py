@@ -654,3 +654,38 @@ def test_fused_epilogue_kernel_vs_autograd(rot, bg):
             close(g, wnt.reshape(g.shape), 1e-4, f"epilogue out[{k}]")
     for k, (g, wnt) in enumerate(zip(res[0][1], res[1][1])):
         close(g, wnt, 2e-3, f"epilogue grad[{k}]")
+
+
+@pytest.mark.parametrize("kind", ["derived_plus_predicted", "purely_predicted", "purely_derived"])
+def test_fused_primary_matches_modular_path(golden_rotated, kind):
+    """The fused primary march (tir_primary_march / _app_list / _heads / _backward: 21 launches, own backward kernels for
+    the heads) against the modular autograd path (one kernel per op, torch / cuBLAS backward of the heads): every map and
+    every parameter gradient, for the three normals kinds."""
+    from tensoir_b200 import Renderer_TensoIR_train
+    fx = golden_rotated
+    rays, li = fx["rays"].to(DEV), fx["light_idx"].to(DEV)
+    outs = []
+    for modular in (True, False):
+        m = model_from_fixture(fx, DEV)
+        m.normals_kind = kind
+        m.__dict__["_tir_modular"] = modular
+        m.__dict__["_tir_randn_like"] = lambda t: torch.sin(t * 977.0)
+        torch.manual_seed(11)
+        got = Renderer_TensoIR_train(rays, None, li, m, N_samples=60, white_bg=True, is_train=True, is_relight=True,
+                                     sample_method='stratified_sampling', device=DEV, args=renderer_args(24))
+        loss = _train_loss(got) + 0.3 * got["acc_map"].mean() + 0.1 * got["depth_map"].mean() \
+            + 0.05 * (got["albedo_map"] ** 2).mean() + 0.05 * (got["roughness_map"] ** 2).mean() \
+            + 0.05 * (got["normal_map"][:, 2]).mean()
+        loss.backward()
+        outs.append((got, loss, {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}))
+    (g0, l0, gr0), (g1, l1, gr1) = outs
+    for k in g0:
+        close(g1[k], g0[k], 2e-5, k)
+    close(l1, l0, 2e-5, "loss")
+    assert set(gr0) == set(gr1), set(gr0) ^ set(gr1)
+    worst = {}
+    for k in gr0:
+        scale = float(gr0[k].abs().max()) + 1e-12
+        worst[k] = float((gr0[k] - gr1[k]).abs().max()) / scale
+    bad = {k: v for k, v in worst.items() if v > 2e-4}
+    assert not bad, bad
