@@ -218,6 +218,26 @@ int tir_shade_bwd(const float* normal, const float* albedo, const float* rough, 
                   const float* g_rgb, float* g_normal, float* g_albedo, float* g_rough, float* g_fresnel,
                   float* g_direct, void* stream);
 
+/* The same quadrature over a WHOLE ray batch masked by acc_mask (renderer.py:99-106): rows with mask == 0 shade to the
+ * constant 1 (white) and contribute no gradient; rows with mask != 0 are shaded, clipped to [0,1] and (srgb != 0)
+ * converted with linear2srgb_torch (relight_utils.py:476-481, :489-515) inside the kernel.  The surface hits are never
+ * compacted into a list: tir_hits_prepare builds the surface points (rays_o + depth * rays_d, relight_utils.py:412) and
+ * zeroes the normals of non-hit rays, which makes tir_secondary_radiance skip all of their directions.
+ *   rays [n,6], mask [n] (0/1), normal/albedo/fresnel [n,3], rough1 [n,1], view direction = -rays_d;
+ *   lin [n,3] = linear value before clip / sRGB (written by the forward, read by the backward). */
+int tir_hits_prepare(const float* rays, const float* depth, const float* normal, const uint8_t* mask, int64_t n,
+                     float* surf_xyz, float* normal_masked, void* stream);
+int tir_shade_hits_fwd(const float* rays, const uint8_t* mask, const float* normal, const float* albedo,
+                       const float* rough1, const float* fresnel, const int32_t* light_idx, int64_t n,
+                       const float* dirs, const float* weight, int32_t n_dirs, const float* direct, int32_t n_lights,
+                       const float* vis, const float* indirect, int32_t srgb, float* rgb, float* lin, void* stream);
+int tir_shade_hits_bwd(const float* rays, const uint8_t* mask, const float* normal, const float* albedo,
+                       const float* rough1, const float* fresnel, const int32_t* light_idx, int64_t n,
+                       const float* dirs, const float* weight, int32_t n_dirs, const float* direct, int32_t n_lights,
+                       const float* vis, const float* indirect, int32_t srgb, const float* lin, const float* g_rgb,
+                       float* g_normal, float* g_albedo, float* g_rough1, float* g_fresnel, float* g_direct,
+                       void* stream);
+
 /* ---- modular, autograd-facing half of the primary march (training needs gradients) --------------------- */
 
 /* plane*line products of the appearance tensors on normalised points: xn [n,3] -> out [n, 3*aC]

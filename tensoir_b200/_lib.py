@@ -120,6 +120,12 @@ EXPORTS = {
                                 C.c_int32, f32p, f32p, f32p, C.c_void_p]),
     "tir_shade_bwd": (C.c_int, [f32p, f32p, f32p, f32p, f32p, C.c_void_p, C.c_int64, f32p, f32p, C.c_int32, f32p,
                                 C.c_int32, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, C.c_void_p]),
+    "tir_hits_prepare": (C.c_int, [f32p, f32p, f32p, C.c_void_p, C.c_int64, f32p, f32p, C.c_void_p]),
+    "tir_shade_hits_fwd": (C.c_int, [f32p, C.c_void_p, f32p, f32p, f32p, f32p, C.c_void_p, C.c_int64, f32p, f32p,
+                                     C.c_int32, f32p, C.c_int32, f32p, f32p, C.c_int32, f32p, f32p, C.c_void_p]),
+    "tir_shade_hits_bwd": (C.c_int, [f32p, C.c_void_p, f32p, f32p, f32p, f32p, C.c_void_p, C.c_int64, f32p, f32p,
+                                     C.c_int32, f32p, C.c_int32, f32p, f32p, C.c_int32, f32p, f32p, f32p, f32p, f32p,
+                                     f32p, f32p, C.c_void_p]),
     "tir_vm_app_products": (C.c_int, [C.POINTER(TirField), f32p, C.c_int64, f32p, C.c_void_p]),
     "tir_vm_app_products_bwd": (C.c_int, [C.POINTER(TirField), f32p, C.c_int64, f32p, C.POINTER(C.c_void_p),
                                           C.POINTER(C.c_void_p), C.c_void_p]),
@@ -162,6 +168,7 @@ KERNELS_PER_CALL = {"tir_pack_channels_last": 1, "tir_unpack_channels_last_add":
                     "tir_shade_fwd": 1, "tir_shade_bwd": 1, "tir_app_mlp_points": 1, "tir_app_mlp_points_save": 1, "tir_vm_app_products": 1, "tir_vm_app_products_bwd": 1,
                     "tir_vm_density_bwd": 1, "tir_vm_density_grad": 1, "tir_vm_density_grad_bwd": 1,
                     "tir_valid_samples_count": 1, "tir_valid_samples_fill": 1, "tir_composite_fwd": 1,
+                    "tir_hits_prepare": 1, "tir_shade_hits_fwd": 1, "tir_shade_hits_bwd": 1,
                     "tir_primary_march": 6, "tir_primary_app_list": 1, "tir_primary_heads": 5,
                     "tir_primary_backward": 9,
                     "tir_composite_bwd": 1, "tir_tail_fwd": 1, "tir_tail_bwd": 1, "tir_epilogue_fwd": 1,

@@ -276,6 +276,7 @@ __global__ void __launch_bounds__(NT, 1) heads_dgrad_kernel(const DgradParams p)
         const int cb = task % 9, rh = task / 9;
         float acc[2][2][4] = {};
         warp_gemm_nt<2>(acc, s.gfh, s.gfl, rh * 32, s.bth, s.btl, SF, cb * 16, 32, lane, SF);
+        float gl[2][2][4];            // d(...) * raw products: the light_line gradient contributions
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -284,12 +285,12 @@ __global__ void __launch_bounds__(NT, 1) heads_dgrad_kernel(const DgradParams p)
             for (int half = 0; half < 2; ++half) {
               const int row = rh * 32 + mt * 16 + g + half * 8, c = cb * 16 + nt * 8 + 2 * t4;
               const int64_t i = base + row;
+              gl[mt][nt][half * 2] = 0.f; gl[mt][nt][half * 2 + 1] = 0.f;
               if (i >= total) continue;
               const float a0 = acc[mt][nt][half * 2], a1 = acc[mt][nt][half * 2 + 1];
               float l0 = 1.f, l1 = 1.f;
-              const int lr = mode == 1 ? s.light[row] : 0;
               if (mode == 1) {
-                const float2 lv = __ldg(reinterpret_cast<const float2*>(mlp.light_line + (size_t)lr * K0 + c));
+                const float2 lv = __ldg(reinterpret_cast<const float2*>(mlp.light_line + (size_t)s.light[row] * K0 + c));
                 l0 = lv.x; l1 = lv.y;
               } else if (mode == 2) {
                 l0 = s.lmean[c]; l1 = s.lmean[c + 1];
@@ -297,15 +298,45 @@ __global__ void __launch_bounds__(NT, 1) heads_dgrad_kernel(const DgradParams p)
               *reinterpret_cast<float2*>(J.gx0 + i * K0 + c) = make_float2(a0 * l0, a1 * l1);
               if (mode != 0) {
                 const float2 xv = __ldg(reinterpret_cast<const float2*>(x0 + i * K0 + c));
-                if (lr < LMAX) {
-                  atomicAdd(&s.glight[lr * K0 + c], a0 * xv.x);
-                  atomicAdd(&s.glight[lr * K0 + c + 1], a1 * xv.y);
-                } else {
-                  atomicAdd(p.sh.g_light + (size_t)lr * K0 + c, a0 * xv.x);
-                  atomicAdd(p.sh.g_light + (size_t)lr * K0 + c + 1, a1 * xv.y);
-                }
+                gl[mt][nt][half * 2] = a0 * xv.x; gl[mt][nt][half * 2 + 1] = a1 * xv.y;
               }
             }
+        if (mode != 0) {
+          // Sum over the warp's 32 rows BEFORE touching shared memory: per light row, add the thread's 4 rows, then
+          // butterfly over the 8 row lanes; lanes g == 0 own distinct columns (no same-address atomics in a warp).
+          const int nl = mode == 2 ? 1 : (L < LMAX ? L : LMAX);
+          for (int l = 0; l < nl; ++l) {
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                float v = 0.f;
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                  for (int half = 0; half < 2; ++half) {
+                    const int row = rh * 32 + mt * 16 + g + half * 8;
+                    if (mode == 2 || s.light[row] == l) v += gl[mt][nt][half * 2 + e];
+                  }
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                v += __shfl_xor_sync(0xffffffffu, v, 8);
+                v += __shfl_xor_sync(0xffffffffu, v, 16);
+                if (g == 0 && v != 0.f) atomicAdd(&s.glight[l * K0 + cb * 16 + nt * 8 + 2 * t4 + e], v);
+              }
+          }
+          if (mode == 1 && L > LMAX) {           // rare: more lights than shared rows -> straight to global memory
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+              for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int row = rh * 32 + mt * 16 + g + (e >> 1) * 8, lr = s.light[row];
+                  if (lr >= LMAX && gl[mt][nt][e] != 0.f)
+                    atomicAdd(p.sh.g_light + (size_t)lr * K0 + cb * 16 + nt * 8 + 2 * t4 + (e & 1), gl[mt][nt][e]);
+                }
+          }
+        }
       }
     }
     __syncthreads();

@@ -115,6 +115,50 @@ def render_with_BRDF(depth_map, normal_map, albedo_map, roughness_map, fresnel_m
                       incident_light_dirs, light_idx, light_area_weight, nlights, sample_method, use_linear2srgb, device)
 
 
+def render_hits(depth_map, normal_map, albedo_map, roughness_map, fresnel_map, acc_mask, rays, tensoIR, light_idx,
+                sample_method='fixed_envirmap', use_linear2srgb=True, args=None):
+    """``rgb_with_brdf`` of Renderer_TensoIR_train (renderer.py:99-106) for the WHOLE ray batch at once:
+        out = ones;  out[acc_mask] = render_with_BRDF(depth_map[acc_mask], ...)
+    without ever compacting the hits: non-hit rays get a zero normal (the secondary march's cosine test then skips all
+    their directions) and shade to the constant 1 inside the fused kernel (csrc/tir_shade.cu, tir_shade_hits_*), which
+    also applies the [0,1] clip and linear2srgb.  Nothing depends on the number of hits, so there is no list to size
+    (or overflow) under CUDA-graph capture, and no boolean-mask gathers / scatters in either direction."""
+    import ctypes as C
+    from . import _lib
+    from .shade import shade_hits
+    device = depth_map.device
+    lib = _lib.load()
+    rays = rays.float().contiguous()
+    n = rays.shape[0]
+    st = tensoIR.__dict__.get("_tir_static")
+    if st is not None:
+        dirs = st["dirs"]                                   # device buffer refilled by the host (same generator order)
+    else:
+        dirs = tensoIR.gen_light_incident_dirs(method=sample_method).to(device)     # host draws, reference order
+    weight = tensoIR.__dict__.get("_tir_area_weight_dev")
+    if weight is None or weight.device != device:
+        weight = tensoIR.light_area_weight.to(device)
+        tensoIR.__dict__["_tir_area_weight_dev"] = weight
+    nl = dirs.shape[0]
+    if sample_method == 'stratifed_sample_equal_areas':
+        weight = torch.full((nl,), 4 * torch.pi / nl, device=device)
+    surf = torch.empty(n, 3, device=device)
+    nrm = torch.empty(n, 3, device=device)
+    with torch.no_grad():
+        nm = normal_map.detach().float().contiguous()
+        _lib.check(lib.tir_hits_prepare(_lib.dptr(rays), _lib.dptr(depth_map.detach().float().contiguous()),
+                                        _lib.dptr(nm), _lib.dptr(acc_mask.contiguous(), torch.bool), n, _lib.dptr(surf),
+                                        _lib.dptr(nrm), _lib.stream_ptr()), "tir_hits_prepare")
+        with record_function("tir::secondary"):
+            vis, indirect, _ = ops.secondary_radiance(
+                tensoIR, surf, nrm, light_idx, dirs, n_sample=args.second_nSample, near=args.second_near,
+                far=args.second_far, counters=tensoIR.__dict__.get("_tir_counters"))
+    direct = tensoIR.get_light_rgbs(dirs, device=device).to(device)            # [L, nl, 3], autograd reaches lgtSGs
+    with record_function("tir::shade_epilogue"):
+        return shade_hits(normal_map, albedo_map, roughness_map, fresnel_map, direct, rays, acc_mask, light_idx, dirs,
+                          weight, vis, indirect, srgb=use_linear2srgb)
+
+
 def _shade(tensoIR, normal_map, albedo_map, roughness_map, fresnel_map, surf2c, vis, indirect, incident_light_dirs,
            light_idx, light_area_weight, nlights, sample_method, use_linear2srgb, device):
     """Quadrature of the rendering equation, relight_utils.py:452-483: fused CUDA kernel (forward + analytic

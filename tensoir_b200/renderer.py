@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import torch
 
-from .relight_utils import render_with_BRDF
+from .relight_utils import render_hits, render_with_BRDF
 
 
 def Renderer_TensoIR_train(rays=None, normal_gt=None, light_idx=None, tensoIR=None, N_samples=-1, ndc_ray=False,
@@ -20,33 +20,11 @@ def Renderer_TensoIR_train(rays=None, normal_gt=None, light_idx=None, tensoIR=No
                 N_samples=N_samples)
     if tensoIR.normals_kind == "gt_normals" and normal_gt is not None:
         normal_map = normal_gt.to(device)
-    if is_relight and tensoIR.__dict__.get("_tir_static") is not None:
-        # shape-static variant (CUDA-graph capture): the acc_mask rows are compacted into a list of STATIC capacity
-        # (padding rows point at a dummy row N, carry a zero normal so the secondary kernel's cosine test skips all
-        # their directions, and are dropped by the scatter), exactly mirroring the dynamic branch below.
-        st = tensoIR.__dict__["_tir_static"]
-        n = rgb_map.shape[0]
-        cap = min(int(st.get("cap_hit", n)), n) if n > 0 else 0
-        idx = torch.nonzero_static(acc_mask, size=cap, fill_value=-1).reshape(-1)
-        real = idx >= 0
-        from .primary import note_count
-        note_count(st, 2, acc_mask.sum(), cap)
-        src = idx.clamp(min=0)
-        keep = real[:, None].to(normal_map.dtype)
-        shaded = render_with_BRDF(depth_map.index_select(0, src), normal_map.index_select(0, src) * keep,
-                                  albedo_map.index_select(0, src), roughness_map.index_select(0, src).repeat(1, 3),
-                                  fresnel_map.index_select(0, src), rays.index_select(0, src), tensoIR,
-                                  light_idx.index_select(0, src), sample_method, chunk_size=chunk_size, device=device,
-                                  args=args)
-        dst = torch.where(real, idx, torch.full_like(idx, n))
-        rgb_with_brdf = torch.ones((n + 1, 3), device=rgb_map.device, dtype=rgb_map.dtype).index_copy(0, dst, shaded)[:n]
-    elif is_relight:
-        masked = render_with_BRDF(depth_map[acc_mask], normal_map[acc_mask], albedo_map[acc_mask],
-                                  roughness_map[acc_mask].repeat(1, 3), fresnel_map[acc_mask], rays[acc_mask],
-                                  tensoIR, light_idx[acc_mask], sample_method, chunk_size=chunk_size,
-                                  device=device, args=args)
-        rgb_with_brdf = torch.ones_like(rgb_map)
-        rgb_with_brdf[acc_mask] = masked
+    if is_relight and rgb_map.shape[0] > 0:
+        # rgb_with_brdf = ones; rgb_with_brdf[acc_mask] = render_with_BRDF(<maps>[acc_mask], ...) (renderer.py:99-106)
+        # evaluated for the whole batch at once, non-hit rays shading to 1 inside the kernel: no list of hits exists
+        rgb_with_brdf = render_hits(depth_map, normal_map, albedo_map, roughness_map, fresnel_map, acc_mask, rays,
+                                    tensoIR, light_idx, sample_method, args=args)
     else:
         rgb_with_brdf = torch.ones_like(rgb_map)
     return {"rgb_map": rgb_map, "depth_map": depth_map, "normal_map": normal_map, "albedo_map": albedo_map,

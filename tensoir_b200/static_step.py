@@ -206,11 +206,12 @@ class StaticTrainStep:
         self._seen = tuple(max(a, b) for a, b in zip(old, (n_valid, n_app, n_hit, n_sec)))
         want = list(caps)
         for i in range(3):
-            if seen[i] > self.grow_at * caps[i] and not (i == 2 and caps[i] >= self.n_rays):
+            if i < 2 and seen[i] > self.grow_at * caps[i]:      # (the surface hits are not a list any more)
                 want[i] = int(self.headroom * seen[i]) + 64
-        sec_cap = self.static["sec_per_slot"] * caps[2] * self.static["dirs"].shape[0]
-        if n_sec > self.grow_at * sec_cap:          # secondary appearance scratch: rows per (hit, direction) slot
-            self.static["sec_per_slot"] = int(self.headroom * n_sec / max(1, caps[2] * self.static["dirs"].shape[0])) + 1
+        slots = self.n_rays * self.static["dirs"].shape[0]
+        sec_cap = max(1 << 16, self.static["sec_per_slot"] * slots)
+        if n_sec > self.grow_at * sec_cap:          # secondary appearance scratch: rows per (ray, direction) slot
+            self.static["sec_per_slot"] = int(self.headroom * n_sec / max(1, slots)) + 1
             return bool(over), tuple(want)
         return bool(over), (None if tuple(want) == caps else tuple(want))
 
