@@ -188,6 +188,24 @@ int tir_app_mlp(const TirField* field, const TirMlp* mlp, const TirAppSample* sa
                 const uint32_t* sample_count, int64_t max_samples, const float* ray_dirs, int32_t n_dirs,
                 const int32_t* light_idx, float* rgb_out, void* stream);
 
+/* The two implementations behind tir_app_mlp (which dispatches to _tc5 unless the environment has TIR_MLP_LEGACY=1):
+ *   _tc5     sm_100a-native: tcgen05.mma with the accumulator and the A operand in tensor memory (TMEM), weights
+ *            resident in shared memory, two warpgroups ping-ponging through one issuer thread (csrc/tir_mlp_tc5.cu)
+ *   _legacy  round 1: mma.sync.m16n8k16 on 64-sample tiles (csrc/tir_mlp.cu)
+ * Same arguments and results (both use the error-compensated split-BF16 product with fp32 accumulation). */
+int tir_app_mlp_tc5(const TirField* field, const TirMlp* mlp, const TirAppSample* samples,
+                    const uint32_t* sample_count, int64_t max_samples, const float* ray_dirs, int32_t n_dirs,
+                    const int32_t* light_idx, float* rgb_out, void* stream);
+int tir_app_mlp_legacy(const TirField* field, const TirMlp* mlp, const TirAppSample* samples,
+                       const uint32_t* sample_count, int64_t max_samples, const float* ray_dirs, int32_t n_dirs,
+                       const int32_t* light_idx, float* rgb_out, void* stream);
+int tir_app_mlp_points_tc5(const TirField* field, const TirMlp* mlp, const float* xn, const float* x_in,
+                           const int32_t* light_idx, int64_t n, int32_t act, float* out, void* stream);
+int tir_app_mlp_points_legacy(const TirField* field, const TirMlp* mlp, const float* xn, const float* x_in,
+                              const int32_t* light_idx, int64_t n, int32_t act, float* out, void* stream);
+/* 0 while no bounded mbarrier wait of the tcgen05 kernel has timed out (host read; synchronises the device). */
+int tir_mlp_tc5_error(void);
+
 /* Same gather+MLP on explicit points (no compositing): xn [n,3] normalised coords, x_in [n,3] the 3-vector fed
  * to the MLP next to the features (view dir for MLPRender_Fea, position for MLPBRDF_PEandFeature),
  * light_idx [n] or NULL (row 0 of mlp->light_line, e.g. the mean-light row of compute_intrinfeature),

@@ -112,6 +112,15 @@ EXPORTS = {
                                       C.c_void_p]),
     "tir_app_mlp": (C.c_int, [C.POINTER(TirField), C.POINTER(TirMlp), C.c_void_p, C.c_void_p, C.c_int64, f32p,
                               C.c_int32, C.c_void_p, f32p, C.c_void_p]),
+    "tir_app_mlp_tc5": (C.c_int, [C.POINTER(TirField), C.POINTER(TirMlp), C.c_void_p, C.c_void_p, C.c_int64, f32p,
+                                  C.c_int32, C.c_void_p, f32p, C.c_void_p]),
+    "tir_app_mlp_legacy": (C.c_int, [C.POINTER(TirField), C.POINTER(TirMlp), C.c_void_p, C.c_void_p, C.c_int64, f32p,
+                                     C.c_int32, C.c_void_p, f32p, C.c_void_p]),
+    "tir_app_mlp_points_tc5": (C.c_int, [C.POINTER(TirField), C.POINTER(TirMlp), f32p, f32p, C.c_void_p, C.c_int64,
+                                         C.c_int32, f32p, C.c_void_p]),
+    "tir_app_mlp_points_legacy": (C.c_int, [C.POINTER(TirField), C.POINTER(TirMlp), f32p, f32p, C.c_void_p, C.c_int64,
+                                            C.c_int32, f32p, C.c_void_p]),
+    "tir_mlp_tc5_error": (C.c_int, []),
     "tir_app_mlp_points": (C.c_int, [C.POINTER(TirField), C.POINTER(TirMlp), f32p, f32p, C.c_void_p, C.c_int64,
                                      C.c_int32, f32p, C.c_void_p]),
     "tir_app_mlp_points_save": (C.c_int, [C.POINTER(TirField), C.POINTER(TirMlp), f32p, f32p, C.c_void_p, C.c_int64,
@@ -164,7 +173,8 @@ EXPORTS = {
 # kernels launched per entry point (for bench.py's gpu_launches claim)
 KERNELS_PER_CALL = {"tir_pack_channels_last": 1, "tir_unpack_channels_last_add": 1, "tir_pack_alpha_mask": 2,
                     "tir_density_points": 1, "tir_alpha_mask_points": 1, "tir_march_density": 1,
-                    "tir_march_radiance": 2, "tir_secondary_march": 1, "tir_secondary_radiance": 2, "tir_app_mlp": 1,
+                    "tir_march_radiance": 2, "tir_secondary_march": 1, "tir_secondary_radiance": 2, "tir_app_mlp": 1, "tir_app_mlp_tc5": 1, "tir_app_mlp_legacy": 1, "tir_app_mlp_points_tc5": 1,
+                    "tir_app_mlp_points_legacy": 1,
                     "tir_shade_fwd": 1, "tir_shade_bwd": 1, "tir_app_mlp_points": 1, "tir_app_mlp_points_save": 1, "tir_vm_app_products": 1, "tir_vm_app_products_bwd": 1,
                     "tir_vm_density_bwd": 1, "tir_vm_density_grad": 1, "tir_vm_density_grad_bwd": 1,
                     "tir_valid_samples_count": 1, "tir_valid_samples_fill": 1, "tir_composite_fwd": 1,

@@ -10,6 +10,7 @@
 // resident in shared memory as split BF16 (176 KB) and stream 64-sample tiles through one in-place activation
 // buffer; fragments are fetched with ldmatrix from rows padded to an odd multiple of 16 bytes (conflict free).
 #include <cuda_bf16.h>
+#include <cstdlib>
 #include "tir_device.cuh"
 #include "tir_internal.h"
 
@@ -394,9 +395,34 @@ int launch(const MlpParams& p, int64_t max_items, cudaStream_t stream) {
 
 }  // namespace
 
+extern "C" int tir_app_mlp_tc5(const TirField* field, const TirMlp* mlp, const TirAppSample* samples,
+                               const uint32_t* sample_count, int64_t max_samples, const float* ray_dirs,
+                               int32_t n_dirs, const int32_t* light_idx, float* rgb_out, void* stream);
+extern "C" int tir_app_mlp_points_tc5(const TirField* field, const TirMlp* mlp, const float* xn, const float* x_in,
+                                      const int32_t* light_idx, int64_t n, int32_t act, float* out, void* stream);
+
+// TIR_MLP_LEGACY=1 selects the round-1 mma.sync kernel for the inference entry points (A/B comparison); the default is
+// the tcgen05 / TMEM kernel of tir_mlp_tc5.cu.  The training forward with activation dumps always uses this file.
+static bool legacy_mlp() {
+  static const bool v = [] { const char* e = getenv("TIR_MLP_LEGACY"); return e && e[0] == '1'; }();
+  return v;
+}
+
+extern "C" int tir_app_mlp_legacy(const TirField* field, const TirMlp* mlp, const TirAppSample* samples,
+                                  const uint32_t* sample_count, int64_t max_samples, const float* ray_dirs,
+                                  int32_t n_dirs, const int32_t* light_idx, float* rgb_out, void* stream);
+
 extern "C" int tir_app_mlp(const TirField* field, const TirMlp* mlp, const TirAppSample* samples,
                            const uint32_t* sample_count, int64_t max_samples, const float* ray_dirs, int32_t n_dirs,
                            const int32_t* light_idx, float* rgb_out, void* stream) {
+  if (!legacy_mlp())
+    return tir_app_mlp_tc5(field, mlp, samples, sample_count, max_samples, ray_dirs, n_dirs, light_idx, rgb_out, stream);
+  return tir_app_mlp_legacy(field, mlp, samples, sample_count, max_samples, ray_dirs, n_dirs, light_idx, rgb_out, stream);
+}
+
+extern "C" int tir_app_mlp_legacy(const TirField* field, const TirMlp* mlp, const TirAppSample* samples,
+                                  const uint32_t* sample_count, int64_t max_samples, const float* ray_dirs,
+                                  int32_t n_dirs, const int32_t* light_idx, float* rgb_out, void* stream) {
   if (!field || !mlp || !samples || !sample_count || !ray_dirs || !rgb_out) return TIR_ERR_NULL;
   int rc = check_shapes(field, mlp);
   if (rc) return rc;
@@ -431,8 +457,17 @@ extern "C" int tir_app_mlp_points_save(const TirField* field, const TirMlp* mlp,
   return launch<true>(p, n, (cudaStream_t)stream);
 }
 
+extern "C" int tir_app_mlp_points_legacy(const TirField* field, const TirMlp* mlp, const float* xn, const float* x_in,
+                                         const int32_t* light_idx, int64_t n, int32_t act, float* out, void* stream);
+
 extern "C" int tir_app_mlp_points(const TirField* field, const TirMlp* mlp, const float* xn, const float* x_in,
                                   const int32_t* light_idx, int64_t n, int32_t act, float* out, void* stream) {
+  if (!legacy_mlp()) return tir_app_mlp_points_tc5(field, mlp, xn, x_in, light_idx, n, act, out, stream);
+  return tir_app_mlp_points_legacy(field, mlp, xn, x_in, light_idx, n, act, out, stream);
+}
+
+extern "C" int tir_app_mlp_points_legacy(const TirField* field, const TirMlp* mlp, const float* xn, const float* x_in,
+                                         const int32_t* light_idx, int64_t n, int32_t act, float* out, void* stream) {
   if (n <= 0) return TIR_OK;   // empty input: nothing to do (pointers of empty tensors are NULL)
   if (!field || !mlp || !xn || !x_in || !out) return TIR_ERR_NULL;
   int rc = check_shapes(field, mlp);

@@ -689,3 +689,54 @@ def test_fused_primary_matches_modular_path(golden_rotated, kind):
         worst[k] = float((gr0[k] - gr1[k]).abs().max()) / scale
     bad = {k: v for k, v in worst.items() if v > 2e-4}
     assert not bad, bad
+
+
+def test_tcgen05_mlp_matches_mma_sync_kernel(rot):
+    """The sm_100a-native appearance MLP (tcgen05.mma, accumulator + activations in TMEM, csrc/tir_mlp_tc5.cu) against
+    the round-1 mma.sync kernel: explicit points for the three heads (ragged sizes incl. a partial tile and an odd
+    number of tiles), and the secondary appearance list; no bounded wait may have timed out."""
+    import ctypes as C
+    from tensoir_b200 import _lib, ops
+    from tensoir_b200.device_field import mlp_struct
+    fx, m = rot
+    lib = _lib.load()
+    f = ops.device_field(m).refresh(m)
+    g = torch.Generator().manual_seed(7)
+    for n in (1, 127, 128, 300, 5000):
+        xn = (torch.rand(n, 3, generator=g) * 1.9 - 0.95).to(DEV)
+        xi = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1).to(DEV)
+        li = torch.zeros(n, dtype=torch.int32, device=DEV)
+        for head, light, act in (("renderModule", "index", 0), ("renderModule_brdf", "mean", 0),
+                                 ("renderModule_normal", "mean", 1)):
+            keep = []
+            mlp = mlp_struct(m, head, keep, light=light)
+            outs = []
+            for fn in (lib.tir_app_mlp_points_legacy, lib.tir_app_mlp_points_tc5):
+                out = torch.full((n, mlp.out_dim), -7.0, device=DEV)
+                _lib.check(fn(C.byref(f), C.byref(mlp), _lib.dptr(xn), _lib.dptr(xi),
+                              _lib.dptr(li, torch.int32) if light == "index" else None, n, act, _lib.dptr(out),
+                              _lib.stream_ptr()), "mlp points")
+                outs.append(out)
+            torch.cuda.synchronize()
+            assert lib.tir_mlp_tc5_error() == 0
+            close(outs[1], outs[0], 2e-5, f"{head} n={n}")
+    # sample-list form on a real secondary march
+    with torch.no_grad():
+        out = m(fx["rays"].to(DEV), fx["light_idx"].to(DEV), is_train=False, is_relight=True, N_samples=-1)
+    rays = fx["rays"].to(DEV)
+    mask = out[9]
+    surf = (rays[:, :3] + out[1][:, None] * rays[:, 3:])[mask]
+    dirs = m.gen_light_incident_dirs(method='fixed_envirmap').to(DEV)
+    st = ops.SecondaryStages(m, surf, out[2][mask], fx["light_idx"].to(DEV)[mask], dirs, n_sample=24)
+    st.march()
+    res = []
+    for fn in (lib.tir_app_mlp_legacy, lib.tir_app_mlp_tc5):
+        st.ind.zero_()
+        _lib.check(fn(C.byref(st.f), C.byref(st.mlp_s), _lib.dptr(st.sc.buf, torch.uint8),
+                      _lib.dptr(st.sc.count, torch.int32), st.sc.capacity, _lib.dptr(st.dr), st.n_dirs,
+                      _lib.dptr(st.li, torch.int32), _lib.dptr(st.ind), _lib.stream_ptr()), "mlp list")
+        res.append(st.ind.clone())
+    torch.cuda.synchronize()
+    assert lib.tir_mlp_tc5_error() == 0
+    assert int(st.sc.count.item()) > 100
+    close(res[1], res[0], 2e-5, "indirect light")
