@@ -43,6 +43,18 @@ __device__ __forceinline__ FloorI floor_fi(float x) {
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
+// 256-bit read-only load (sm_100a LDG.E.256): one whole 32-byte sector per lane and request.  Channel-last rows are
+// multiples of 64 B, so a bilinear tap of 16 channels is two of these instead of four 128-bit loads that touch every
+// sector twice (half the L1 tag lookups / wavefronts of the gather-bound kernels).  `p` must be 32-byte aligned.
+struct Float8 { float4 a, b; };
+__device__ __forceinline__ Float8 ldg8(const float* p) {
+  Float8 r;
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w)
+               : "l"(p));
+  return r;
+}
+
 struct Bilinear {
   int o00, o01, o10, o11;   // element offsets (texel index, not yet multiplied by C)
   float nw, ne, sw, se;     // weights, zeroed for out-of-bounds taps (zero padding)
@@ -128,13 +140,21 @@ __device__ __forceinline__ float density_feature(const TirField& f, float x, flo
     const float* l1 = L + (size_t)l.o1 * C;
     float s = 0.f;
 #pragma unroll
-    for (int c = 0; c < C; c += 4) {
-      const float4 pv = bilerp4(ldg4(p00 + c), ldg4(p01 + c), ldg4(p10 + c), ldg4(p11 + c), b);
-      const float4 lv = lerp4(ldg4(l0 + c), ldg4(l1 + c), l);
+    for (int c = 0; c < C; c += 8) {          // C is a multiple of 8 for every shipped config (16); same summation order
+      const Float8 t00 = ldg8(p00 + c), t01 = ldg8(p01 + c), t10 = ldg8(p10 + c), t11 = ldg8(p11 + c);
+      const Float8 u0 = ldg8(l0 + c), u1 = ldg8(l1 + c);
+      const float4 pv = bilerp4(t00.a, t01.a, t10.a, t11.a, b);
+      const float4 lv = lerp4(u0.a, u1.a, l);
       s = __fadd_rn(s, __fmul_rn(pv.x, lv.x));
       s = __fadd_rn(s, __fmul_rn(pv.y, lv.y));
       s = __fadd_rn(s, __fmul_rn(pv.z, lv.z));
       s = __fadd_rn(s, __fmul_rn(pv.w, lv.w));
+      const float4 pw = bilerp4(t00.b, t01.b, t10.b, t11.b, b);
+      const float4 lw = lerp4(u0.b, u1.b, l);
+      s = __fadd_rn(s, __fmul_rn(pw.x, lw.x));
+      s = __fadd_rn(s, __fmul_rn(pw.y, lw.y));
+      s = __fadd_rn(s, __fmul_rn(pw.z, lw.z));
+      s = __fadd_rn(s, __fmul_rn(pw.w, lw.w));
     }
     total = __fadd_rn(total, s);
   }

@@ -30,7 +30,6 @@ namespace {
 constexpr int AC = 48;
 constexpr int K0 = 3 * AC;        // 144
 constexpr int F = 27;
-constexpr int FP = 28;            // basis^T row stride (floats)
 constexpr int HID = 128;
 constexpr int IN = 150;
 constexpr int K1 = 160;           // IN padded to k16
@@ -45,7 +44,8 @@ struct Smem5 {
   uint8_t w0l[HID * K1 * 2];
   uint8_t w1h[HID * HID * 2];
   uint8_t w1l[HID * HID * 2];
-  float basisT[K0 * FP];          // [c][f]: one broadcast row per product channel
+  uint8_t bsh[32 * K0 * 2];       // basis_mat as a B operand: [n = feature (27 -> 32)][k = product channel], 32-row atoms
+  uint8_t bsl[32 * K0 * 2];
   float w2[4 * HID];
   float b0[HID], b1[HID], b2[4];
   float lmean[K0];
@@ -80,10 +80,11 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ uint32_t operand_offset(int r, int k) {
   return (uint32_t)(k >> 3) * (uint32_t)(ROWS * 16) + (uint32_t)r * 16u + (uint32_t)(k & 7) * 2u;
 }
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {      // SWIZZLE_NONE, LBO = 2048 B, SBO = 128 B
+// SWIZZLE_NONE descriptor: LBO = bytes between K chunks (= operand rows * 16), SBO = 128 B between 8-row groups
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo = ROWS * 16) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
-  d |= (uint64_t)(((uint32_t)(ROWS * 16) >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
   d |= (uint64_t)((128u >> 4) & 0x3FFFu) << 32;
   d |= (uint64_t)1 << 46;
   return d;
@@ -146,6 +147,18 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// 256-bit read-only load (sm_100: LDG.E.256): one full 32-byte sector per lane and request.  The 128-bit form fetched
+// every sector twice (two requests per sector, second one usually an L1 miss: 88 KB of L1 vs ~200 KB of loads in flight),
+// which put the kernel on the L2 bandwidth wall at 2x the algorithmic bytes.
+struct F8 { float4 a, b; };
+__device__ __forceinline__ F8 ldg8(const float* p) {
+  F8 r;
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w)
+               : "l"(p));
+  return r;
+}
+
 // fp32 pair -> packed split-BF16 words: hi = (bf16(a) | bf16(b) << 16), lo = the residuals
 __device__ __forceinline__ void split_pack(float a, float b, uint32_t& hi, uint32_t& lo) {
   const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
@@ -194,9 +207,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) app_mlp_tc5_kernel(const Tc5Param
     *reinterpret_cast<__nv_bfloat16*>(s.w1h + operand_offset(n, k)) = h;
     *reinterpret_cast<__nv_bfloat16*>(s.w1l + operand_offset(n, k)) = l;
   }
-  for (int i = tid; i < K0 * FP; i += NTHREADS) {
-    const int c = i / FP, f = i % FP;
-    s.basisT[i] = f < F ? __ldg(mlp.basis + f * K0 + c) : 0.f;
+  for (int i = tid; i < 32 * K0; i += NTHREADS) {
+    const int n = i / K0, k = i % K0;
+    const float v = n < F ? __ldg(mlp.basis + n * K0 + k) : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v), l = __float2bfloat16_rn(v - __bfloat162float(h));
+    const uint32_t off = (uint32_t)(k >> 3) * (32u * 16u) + (uint32_t)n * 16u + (uint32_t)(k & 7) * 2u;
+    *reinterpret_cast<__nv_bfloat16*>(s.bsh + off) = h;
+    *reinterpret_cast<__nv_bfloat16*>(s.bsl + off) = l;
   }
   for (int i = tid; i < 4 * HID; i += NTHREADS) s.w2[i] = (i / HID) < out_dim ? __ldg(mlp.w2 + i) : 0.f;
   for (int i = tid; i < HID; i += NTHREADS) { s.b0[i] = __ldg(mlp.b0 + i); s.b1[i] = __ldg(mlp.b1 + i); }
@@ -233,11 +250,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) app_mlp_tc5_kernel(const Tc5Param
   if (warp == NCONS / 32) {
     // =================================================== issuer ===================================================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(ROWS, HID);
+      const uint32_t idesc = make_idesc(ROWS, HID), idesc_b = make_idesc(ROWS, 32);
       uint32_t ph_a[2] = {0, 0}, ph_q = 1;     // a fresh mbarrier passes a wait on parity 1: Q starts out free
       bool ok = true;
       for (int64_t pair = blockIdx.x; pair < n_pairs && ok; pair += gridDim.x) {
-        for (int layer = 0; layer < 2 && ok; ++layer)
+        // stage 0: basis_mat (K = 144, N = 32), 1: layer 0 (K = 160, N = 128), 2: layer 1 (K = 128, N = 128)
+        for (int stage = 0; stage < 3 && ok; ++stage)
           for (int g = 0; g < 2 && ok; ++g) {
             ok = ok && bar_wait(&s.bar_a[g], ph_a[g], p.error);
             ph_a[g] ^= 1;
@@ -246,16 +264,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) app_mlp_tc5_kernel(const Tc5Param
             if (!ok) break;
             tc_fence_after();
             const uint32_t pa = tmem + (uint32_t)g * P_COLS;
-            const int ksteps = layer == 0 ? K1 / 16 : HID / 16;
-            const uint32_t lo_off = layer == 0 ? K1 / 2 : HID / 2;          // hi half | lo half of the A operand
-            const uint8_t* bh = layer == 0 ? s.w0h : s.w1h;
-            const uint8_t* bl = layer == 0 ? s.w0l : s.w1l;
-            for (int ks = 0; ks < ksteps; ++ks) {
-              const uint32_t koff = (uint32_t)ks * 2u * (uint32_t)(ROWS * 16);     // two 8-element K chunks per MMA
-              const uint64_t dh = make_desc(smem_u32(bh) + koff), dl = make_desc(smem_u32(bl) + koff);
-              mma_ts(tmem + Q_OFF, pa + lo_off + ks * 8, dh, idesc, ks > 0);       // small terms first
-              mma_ts(tmem + Q_OFF, pa + ks * 8, dl, idesc, 1);
-              mma_ts(tmem + Q_OFF, pa + ks * 8, dh, idesc, 1);
+            const int kdim = stage == 0 ? K0 : (stage == 1 ? K1 : HID);
+            const uint32_t lo_off = kdim / 2;                                // hi half | lo half of the A operand
+            const uint8_t* bh = stage == 0 ? s.bsh : (stage == 1 ? s.w0h : s.w1h);
+            const uint8_t* bl = stage == 0 ? s.bsl : (stage == 1 ? s.w0l : s.w1l);
+            const uint32_t lbo = stage == 0 ? 32u * 16u : (uint32_t)(ROWS * 16);
+            const uint32_t id = stage == 0 ? idesc_b : idesc;
+            for (int ks = 0; ks < kdim / 16; ++ks) {
+              const uint32_t koff = (uint32_t)ks * 2u * lbo;                 // two 8-element K chunks per MMA
+              const uint64_t dh = make_desc(smem_u32(bh) + koff, lbo), dl = make_desc(smem_u32(bl) + koff, lbo);
+              mma_ts(tmem + Q_OFF, pa + lo_off + ks * 8, dh, id, ks > 0);    // small terms first
+              mma_ts(tmem + Q_OFF, pa + ks * 8, dl, id, 1);
+              mma_ts(tmem + Q_OFF, pa + ks * 8, dh, id, 1);
             }
             mma_commit(&s.bar_d[g]);
           }
@@ -289,50 +309,65 @@ __global__ void __launch_bounds__(NTHREADS, 1) app_mlp_tc5_kernel(const Tc5Param
           li = p.light_idx ? __ldg(p.light_idx + (p.n_dirs > 0 ? ray / p.n_dirs : ray)) : 0;
         }
       }
-      // ---- gather (plane * line * light) and basis_mat in fp32:  feat = basis @ products
-      float feat[F];
-#pragma unroll
-      for (int f = 0; f < F; ++f) feat[f] = 0.f;
-      if (live) {
+      // ---- gather: products (plane * line * light) go straight into P_g as the split-BF16 A operand of the basis GEMM
+#pragma unroll 1
+      for (int k = 0; k < 3; ++k) {
+        const int m0 = kMat0[k], m1 = kMat1[k], v = kVec[k];
+        const Bilinear b = bilinear_setup(xn[m0], xn[m1], p.f.grid[m0], p.f.grid[m1]);
+        const Linear1 l = linear_setup(xn[v], p.f.grid[v]);
+        const float* P00 = p.f.aplane[k] + (size_t)b.o00 * AC;
+        const float* P01 = p.f.aplane[k] + (size_t)b.o01 * AC;
+        const float* P10 = p.f.aplane[k] + (size_t)b.o10 * AC;
+        const float* P11 = p.f.aplane[k] + (size_t)b.o11 * AC;
+        const float* L0 = p.f.aline[k] + (size_t)l.o0 * AC;
+        const float* L1 = p.f.aline[k] + (size_t)l.o1 * AC;
         const float* lrow = p.light_mode == 1 ? (mlp.light_line + (size_t)li * K0) : nullptr;
 #pragma unroll 1
-        for (int k = 0; k < 3; ++k) {
-          const int m0 = kMat0[k], m1 = kMat1[k], v = kVec[k];
-          const Bilinear b = bilinear_setup(xn[m0], xn[m1], p.f.grid[m0], p.f.grid[m1]);
-          const Linear1 l = linear_setup(xn[v], p.f.grid[v]);
-          const float* P00 = p.f.aplane[k] + (size_t)b.o00 * AC;
-          const float* P01 = p.f.aplane[k] + (size_t)b.o01 * AC;
-          const float* P10 = p.f.aplane[k] + (size_t)b.o10 * AC;
-          const float* P11 = p.f.aplane[k] + (size_t)b.o11 * AC;
-          const float* L0 = p.f.aline[k] + (size_t)l.o0 * AC;
-          const float* L1 = p.f.aline[k] + (size_t)l.o1 * AC;
-#pragma unroll 3
-          for (int c = 0; c < AC; c += 4) {
-            const float4 pv = bilerp4(ldg4(P00 + c), ldg4(P01 + c), ldg4(P10 + c), ldg4(P11 + c), b);
-            const float4 lv = lerp4(ldg4(L0 + c), ldg4(L1 + c), l);
-            float x[4] = {__fmul_rn(pv.x, lv.x), __fmul_rn(pv.y, lv.y), __fmul_rn(pv.z, lv.z), __fmul_rn(pv.w, lv.w)};
-            const int col = k * AC + c;
-            if (p.light_mode == 1) {            // (plane * line) * light  (tensoRF_rotated_lights.py:222)
-              const float4 lc = ldg4(lrow + col);
-              x[0] = __fmul_rn(x[0], lc.x); x[1] = __fmul_rn(x[1], lc.y); x[2] = __fmul_rn(x[2], lc.z); x[3] = __fmul_rn(x[3], lc.w);
-            } else if (p.light_mode == 2) {
-              x[0] = __fmul_rn(x[0], s.lmean[col]); x[1] = __fmul_rn(x[1], s.lmean[col + 1]);
-              x[2] = __fmul_rn(x[2], s.lmean[col + 2]); x[3] = __fmul_rn(x[3], s.lmean[col + 3]);
-            }
+        for (int ks = 0; ks < AC / 16; ++ks) {        // 16 channels = one K step = 24 independent LDG.128
+          uint32_t hi[8], lo[8];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float4* bt = reinterpret_cast<const float4*>(s.basisT + (col + e) * FP);   // warp-wide broadcast
+          for (int h8 = 0; h8 < 2; ++h8) {
+            const int c = ks * 16 + h8 * 8;
+            float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (live) {
+              const F8 t00 = ldg8(P00 + c), t01 = ldg8(P01 + c), t10 = ldg8(P10 + c), t11 = ldg8(P11 + c);
+              const F8 u0 = ldg8(L0 + c), u1 = ldg8(L1 + c);
+              const float4 pa = bilerp4(t00.a, t01.a, t10.a, t11.a, b), pb = bilerp4(t00.b, t01.b, t10.b, t11.b, b);
+              const float4 la = lerp4(u0.a, u1.a, l), lb = lerp4(u0.b, u1.b, l);
+              x[0] = __fmul_rn(pa.x, la.x); x[1] = __fmul_rn(pa.y, la.y); x[2] = __fmul_rn(pa.z, la.z); x[3] = __fmul_rn(pa.w, la.w);
+              x[4] = __fmul_rn(pb.x, lb.x); x[5] = __fmul_rn(pb.y, lb.y); x[6] = __fmul_rn(pb.z, lb.z); x[7] = __fmul_rn(pb.w, lb.w);
+              const int col = k * AC + c;
+              if (p.light_mode == 1) {            // (plane * line) * light  (tensoRF_rotated_lights.py:222)
+                const F8 lc = ldg8(lrow + col);
+                x[0] = __fmul_rn(x[0], lc.a.x); x[1] = __fmul_rn(x[1], lc.a.y); x[2] = __fmul_rn(x[2], lc.a.z); x[3] = __fmul_rn(x[3], lc.a.w);
+                x[4] = __fmul_rn(x[4], lc.b.x); x[5] = __fmul_rn(x[5], lc.b.y); x[6] = __fmul_rn(x[6], lc.b.z); x[7] = __fmul_rn(x[7], lc.b.w);
+              } else if (p.light_mode == 2) {
 #pragma unroll
-              for (int q = 0; q < 7; ++q) {
-                const float4 w4 = bt[q];
-                feat[q * 4] = fmaf(x[e], w4.x, feat[q * 4]);
-                if (q * 4 + 1 < F) feat[q * 4 + 1] = fmaf(x[e], w4.y, feat[q * 4 + 1]);
-                if (q * 4 + 2 < F) feat[q * 4 + 2] = fmaf(x[e], w4.z, feat[q * 4 + 2]);
-                if (q * 4 + 3 < F) feat[q * 4 + 3] = fmaf(x[e], w4.w, feat[q * 4 + 3]);
+                for (int e = 0; e < 8; ++e) x[e] = __fmul_rn(x[e], s.lmean[col + e]);
               }
             }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) split_pack(x[2 * e], x[2 * e + 1], hi[h8 * 4 + e], lo[h8 * 4 + e]);
           }
+          tmem_st8(tp + (k * (AC / 16) + ks) * 8, hi);
+          tmem_st8(tp + K0 / 2 + (k * (AC / 16) + ks) * 8, lo);
         }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      bar_arrive(&s.bar_a[g]);
+      // ---- basis_mat on the tensor cores: feat = products @ basis^T (27 of 32 accumulator columns)
+      float feat[F];
+      {
+        ok = ok && bar_wait(&s.bar_d[g], ph_d, p.error);
+        ph_d ^= 1;
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld32(tq, v);
+#pragma unroll
+        for (int f = 0; f < F; ++f) feat[f] = __uint_as_float(v[f]);
+        tc_fence_before();
+        bar_arrive(&s.bar_q);        // Q drained
       }
       // ---- positional encoding -> the 160-wide input row, written as the split-BF16 A operand into P_g
       {
