@@ -3,7 +3,22 @@ the evaluation loops (I/O + metrics, out of scope) are taken from the reference'
 importable further down sys.path."""
 import importlib.util
 import os
+import random  # noqa: F401  (the train scripts take np / random / os / tqdm / torch from `from renderer import *`)
 import sys
+
+import numpy as np  # noqa: F401
+import torch  # noqa: F401
+from tqdm.auto import tqdm  # noqa: F401
+
+try:                                   # renderer.py:5 `from utils import *`: the reference's own helpers (N_to_reso,
+    from utils import *  # noqa: F401,F403   cal_n_samples, TVLoss, ...), resolved from the reference tree on sys.path
+except ImportError:
+    pass
+try:
+    import imageio  # noqa: F401
+    import torchvision.utils as vutils  # noqa: F401
+except ImportError:
+    pass
 
 from tensoir_b200.renderer import Renderer_TensoIR_train, OctreeRender_trilinear_fast  # noqa: F401
 from tensoir_b200.relight_utils import render_with_BRDF  # noqa: F401
