@@ -216,6 +216,9 @@ class StaticTrainStep:
         return bool(over), (None if tuple(want) == caps else tuple(want))
 
     def _recapture(self, caps):
+        import sys
+        sys.stderr.write(f"StaticTrainStep: re-capture, lists {self.capacities()} -> {tuple(caps)}, secondary rows per "
+                         f"slot {self.static['sec_per_slot']}, longest seen {getattr(self, '_seen', None)}\n")
         self.graph = None
         before = (self.capacities(), self.static["sec_per_slot"])
         self._set_caps(*caps)

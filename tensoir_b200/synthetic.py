@@ -148,7 +148,8 @@ def training_batch(poses: torch.Tensor, batch: int, step: int, H: int = 800, W: 
     return rays, light
 
 
-def make_lego_model(grid: int, device, *, lights=("000",), general=False, mask_res=None, seed: int = SEED):
+def make_lego_model(grid: int, device, *, lights=("000",), general=False, mask_res=None, seed: int = SEED,
+                    envmap=(16, 32)):
     """The benchmark field: TensorVMSplit at ``grid``^3 on aabb +-1.5 with the lego box density installed,
     reference initialisation for everything else (appearance 0.1*N(0,1), MLPs / basis / light_line / lgtSGs at
     their default init under ``seed``), and an alpha mask from updateAlphaMask (<= 256^3, train_tensoIR.py:385-389)."""
@@ -158,7 +159,7 @@ def make_lego_model(grid: int, device, *, lights=("000",), general=False, mask_r
     kw = dict(density_n_comp=[16] * 3, appearance_n_comp=[48] * 3, app_dim=27, near_far=[2.0, 6.0],
               shadingMode='MLP_Fea', alphaMask_thres=0.001, density_shift=-10, distance_scale=25, pos_pe=2, view_pe=2,
               fea_pe=2, featureC=128, step_ratio=0.5, fea2denseAct='softplus', normals_kind='derived_plus_predicted',
-              light_kind='sg', numLgtSGs=128)
+              light_kind='sg', numLgtSGs=128, envmap_h=int(envmap[0]), envmap_w=int(envmap[1]))
     if general:
         kw["light_name_list"] = list(lights)
     else:
