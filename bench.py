@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--cpu-rays", type=int, default=1024, help="bounded CPU-baseline sample (primary rays / step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="do not capture the step into a CUDA graph")
+    ap.add_argument("--torch-adam", dest="torch_adam", action="store_true",
+                    help="torch.optim.Adam(fused=True) + autograd density_L1 instead of tensoir_b200.optim.FusedAdam")
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
                     help="BASELINE.json configs index + 1: 2 single light (default, the metric's config), 3 rotated "
                          "multi-light with --envmap_h x --envmap_w secondary directions, 4 general multi-light, 5 relight pass")
@@ -61,11 +63,16 @@ class Args:   # the three fields render_with_BRDF reads from the train scripts' 
     second_nSample, second_near, second_far = 96, 0.05, 1.5
 
 
-def loss_of(ret, target, model, it=0):
+L1_WEIGHT = 4e-5      # L1_weight_rest (configs/single_light/armadillo.txt)
+
+
+def loss_of(ret, target, model, it=0, l1_in_optimizer=False):
     """Loss assembly of the relight phase, train_tensoIR.py:262-312 (TV is switched off once relight starts,
-    :396-399; weights from configs/single_light/armadillo.txt)."""
+    :396-399; weights from configs/single_light/armadillo.txt).  With ``l1_in_optimizer`` the L1_weight_rest *
+    density_L1 term is applied by tensoir_b200.optim.FusedAdam (same gradient, folded into the optimiser pass)."""
     loss = torch.mean((ret['rgb_map'] - target) ** 2)
-    loss = loss + 4e-5 * model.density_L1()
+    if not l1_in_optimizer:
+        loss = loss + L1_WEIGHT * model.density_L1()
     loss = loss + 0.2 * torch.mean((ret['rgb_with_brdf_map'] - target) ** 2)
     loss = loss + 0.0005 * ret['normals_diff_map'].mean() + 0.001 * ret['normals_orientation_loss_map'].mean()
     loss = loss + 0.001 * ret['roughness_smoothness_loss'] + 0.001 * ret['albedo_smoothness_loss']
@@ -147,7 +154,7 @@ def workload_config(a, parallelism):
     return {"workload": f"relight training step, lego-shaped synthetic scene ({what}): "
                         f"TensorVMSplit {a.grid}^3 (16/48 comps, 3 MLP heads, SG light), batch {a.batch} rays of "
                         f"100 views 800x800, N_samples {n_samples_for(a.grid)}, {getattr(a, 'envmap_h', 16)}x"
-                        f"{getattr(a, 'envmap_w', 32)} stratified secondary dirs x 96 samples, fwd+bwd+Adam(fused)",
+                        f"{getattr(a, 'envmap_w', 32)} stratified secondary dirs x 96 samples, fwd+bwd+Adam (one fused pass incl. the L1 regulariser)",
             "global_batch_rays": a.batch * (max(1, a.gpus) if getattr(a, "scaling", "weak") == "weak" else 1),
             "grid": a.grid, "parallelism": parallelism,
             "l2": "inputs change every step (new ray batch, updated parameters); VM tensors "
@@ -274,8 +281,18 @@ def measure(a, model, n_lights, rank, world, local, dev, scaling, with_e2e, cloc
         params += [gp] if isinstance(gp, torch.Tensor) else list(gp)     # a bare Parameter must not be iterated
     # same optimiser and hyper-parameters as train_tensoIR.py:206; fused=True selects PyTorch's single-kernel
     # multi-tensor implementation of the identical update
-    opt = torch.optim.Adam(model.get_optparam_groups(0.02, 0.001), betas=(0.9, 0.99), fused=True,
-                           capturable=not a.eager)
+    fused_opt = not a.torch_adam
+    if fused_opt:
+        # tensoir_b200.optim.FusedAdam: the same Adam update in one launch over all parameters, + the density L1
+        # regulariser's gradient + clearing the gradients
+        from tensoir_b200.optim import FusedAdam
+        from tensoir_b200.static_step import lr_tensors
+        groups = model.get_optparam_groups(0.02, 0.001)
+        opt = FusedAdam(groups if a.eager else lr_tensors(groups, dev), betas=(0.9, 0.99))
+        opt.density_l1(model, L1_WEIGHT)
+    else:
+        opt = torch.optim.Adam(model.get_optparam_groups(0.02, 0.001), betas=(0.9, 0.99), fused=True,
+                               capturable=not a.eager)
     bucket = GradBucket(params) if world > 1 else None
     poses = hemisphere_poses(100)
     n_s = n_samples_for(a.grid)
@@ -302,7 +319,8 @@ def measure(a, model, n_lights, rank, world, local, dev, scaling, with_e2e, cloc
     if not a.eager:
         # whole-step CUDA graph: static-capacity sample lists, host randoms staged into device buffers, replay
         from tensoir_b200.static_step import StaticTrainStep
-        graphed = StaticTrainStep(model, opt, per_rank, n_s, Args, lambda ret, m: loss_of(ret, target, m),
+        graphed = StaticTrainStep(model, opt, per_rank, n_s, Args,
+                                  lambda ret, m: loss_of(ret, target, m, l1_in_optimizer=fused_opt),
                                   grad_bucket=bucket, device=dev)
         # lists sized from 8 batches x 1.5; they grow by themselves (high-water marks, re-capture) and a replay whose
         # lists did not fit is an exact no-op that is redone (static_step.py) - never a silently different step
@@ -315,7 +333,7 @@ def measure(a, model, n_lights, rank, world, local, dev, scaling, with_e2e, cloc
         ret = Renderer_TensoIR_train(rays, None, li, model, N_samples=n_s, white_bg=True, is_train=True,
                                      is_relight=True, sample_method='stratified_sampling', chunk_size=160000,
                                      device=dev, args=Args)
-        loss = loss_of(ret, target, model)
+        loss = loss_of(ret, target, model, l1_in_optimizer=fused_opt)
         opt.zero_grad(set_to_none=False)
         loss.backward()
         if bucket is not None:

@@ -417,6 +417,24 @@ int tir_primary_backward(const TirField* field, const TirHeadJob* jobs, int32_t 
                          const float* g_acc_map /* [n_rays] or NULL */, const float* g_loss_albedo,
                          const float* g_loss_rough, const TirPrimaryGrads* grads, void* stream);
 
+/* ---- optimiser pass: torch.optim.Adam's update for a list of dense fp32 tensors in ONE launch, with
+ * the L1 regulariser's gradient (l1 * sign(param), density_L1 of tensoRF_rotated_lights.py:74-78) folded in, the
+ * gradient cleared for the next accumulation, and a device-side skip flag (found_inf != 0: parameters, moments and the
+ * step counter stay untouched, gradients are still cleared).  table / chunk_prefix / state live in device memory:
+ * chunk_prefix[k] = first chunk (of tir_adam_chunk_elems() elements) of tensor k, state = {step, 1-beta1^t,
+ * sqrt(1-beta2^t), skipped}. */
+typedef struct TirAdamTensor {
+  float* p; float* g; float* m; float* v;   /* parameter, gradient, exp_avg, exp_avg_sq: same dense layout, n elements */
+  int64_t n;
+  const float* lr_dev;                      /* learning rate in device memory (CUDA-graph replay), or NULL -> lr */
+  float lr;
+  float l1;                                 /* coefficient of sign(param) added to the gradient (0: none) */
+} TirAdamTensor;
+int tir_adam_chunk_elems(void);
+int tir_adam_step(const TirAdamTensor* table_dev, int32_t n_tensors, const int64_t* chunk_prefix_dev,
+                  int64_t total_chunks, float* state_dev, float beta1, float beta2, float eps,
+                  const float* found_inf_dev, int32_t clear_grad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

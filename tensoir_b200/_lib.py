@@ -53,6 +53,11 @@ MARCH_NO_BBOX = 1
 MARCH_LEAN_COUNTERS = 2
 
 
+class TirAdamTensor(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("n", C.c_int64),
+                ("lr_dev", C.c_void_p), ("lr", C.c_float), ("l1", C.c_float)]
+
+
 class TirRayMaps(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("rgb", "depth", "normal", "albedo", "rough", "fresnel", "nd", "no")]
 
@@ -129,6 +134,9 @@ EXPORTS = {
                                 C.c_int32, f32p, f32p, f32p, C.c_void_p]),
     "tir_shade_bwd": (C.c_int, [f32p, f32p, f32p, f32p, f32p, C.c_void_p, C.c_int64, f32p, f32p, C.c_int32, f32p,
                                 C.c_int32, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, C.c_void_p]),
+    "tir_adam_chunk_elems": (C.c_int, []),
+    "tir_adam_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_float, C.c_float, C.c_float,
+                                C.c_void_p, C.c_int32, C.c_void_p]),
     "tir_hits_prepare": (C.c_int, [f32p, f32p, f32p, C.c_void_p, C.c_int64, f32p, f32p, C.c_void_p]),
     "tir_shade_hits_fwd": (C.c_int, [f32p, C.c_void_p, f32p, f32p, f32p, f32p, C.c_void_p, C.c_int64, f32p, f32p,
                                      C.c_int32, f32p, C.c_int32, f32p, f32p, C.c_int32, f32p, f32p, C.c_void_p]),
@@ -178,7 +186,7 @@ KERNELS_PER_CALL = {"tir_pack_channels_last": 1, "tir_unpack_channels_last_add":
                     "tir_shade_fwd": 1, "tir_shade_bwd": 1, "tir_app_mlp_points": 1, "tir_app_mlp_points_save": 1, "tir_vm_app_products": 1, "tir_vm_app_products_bwd": 1,
                     "tir_vm_density_bwd": 1, "tir_vm_density_grad": 1, "tir_vm_density_grad_bwd": 1,
                     "tir_valid_samples_count": 1, "tir_valid_samples_fill": 1, "tir_composite_fwd": 1,
-                    "tir_hits_prepare": 1, "tir_shade_hits_fwd": 1, "tir_shade_hits_bwd": 1,
+                    "tir_adam_step": 2, "tir_hits_prepare": 1, "tir_shade_hits_fwd": 1, "tir_shade_hits_bwd": 1,
                     "tir_primary_march": 6, "tir_primary_app_list": 1, "tir_primary_heads": 5,
                     "tir_primary_backward": 9,
                     "tir_composite_bwd": 1, "tir_tail_fwd": 1, "tir_tail_bwd": 1, "tir_epilogue_fwd": 1,

@@ -229,7 +229,23 @@ class _PrimaryRelight(torch.autograd.Function):
         b = ws.bwd_struct(n_jobs)
         gr = TirPrimaryGrads()
         vm = list(model.density_plane) + list(model.density_line) + list(model.app_plane) + list(model.app_line)
-        bufs, views = zip(*[_cl_zeros(p) for p in vm])
+        # Gradient buffers of the VM factors (17-31 M floats).  When a parameter already HAS a dense channel-last .grad
+        # (kept zeroed in place by tensoir_b200.optim.FusedAdam, or the views of a dp.GradBucket) the kernels accumulate
+        # straight into it and autograd gets None for that input: no 70 MB allocation + memset + AccumulateGrad pass per
+        # step.  Otherwise a zeroed buffer in the kernels' layout is returned the usual way.
+        bufs, views = [], []
+        for p in vm:
+            g = p.grad
+            if (g is not None and g.dtype == torch.float32 and g.shape == p.shape and p.shape[0] == 1
+                    and all(a == b for a, b, n in zip(g.stride(), p.stride(), p.shape) if n > 1)
+                    and p.is_contiguous(memory_format=torch.channels_last)
+                    and model.__dict__.get("_tir_grad_inplace", True)):
+                bufs.append(g)
+                views.append(None)
+            else:
+                b_, v_ = _cl_zeros(p)
+                bufs.append(b_)
+                views.append(v_)
         for k in range(3):
             gr.dplane[k], gr.dline[k] = bufs[k].data_ptr(), bufs[3 + k].data_ptr()
             gr.aplane[k], gr.aline[k] = bufs[6 + k].data_ptr(), bufs[9 + k].data_ptr()

@@ -146,16 +146,19 @@ class StaticTrainStep:
         self._stream = s
         self.force_skip.fill_(1.0)
         s.wait_stream(torch.cuda.current_stream())
+        # FusedAdam(clear_grad=True) keeps every gradient zeroed IN PLACE: the buffers created by the first warm-up step
+        # are the ones the captured kernels accumulate into (no per-step allocation / memset / AccumulateGrad pass)
+        keep_grads = bool(getattr(self.opt, "clear_grad", False))
         with torch.cuda.stream(s):
-            for _ in range(warmup):
+            for _ in range(max(warmup, 1)):
                 self._stage_host_randoms(self._slots[0])
-                self.opt.zero_grad(set_to_none=True)
+                self.opt.zero_grad(set_to_none=not keep_grads)
                 self._body()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self._stage_host_randoms(self._slots[0])
         self.graph = torch.cuda.CUDAGraph()
-        self.opt.zero_grad(set_to_none=True)
+        self.opt.zero_grad(set_to_none=not keep_grads)
         l0 = _lib.launch_count
         with torch.cuda.graph(self.graph, stream=s, capture_error_mode=capture_error_mode):
             self.loss = self._body()

@@ -874,7 +874,9 @@ def test_graph_replay_tracks_eager_training_for_50_steps():
     assert float(rel) < 2e-3, float(rel)
     for k in p0:
         d = float((p0[k] - p1[k]).abs().max())
-        assert d <= 2e-2 * max(float(p0[k].abs().max()), 1e-2), (k, d)
+        # Adam divides by sqrt(v): entries whose gradients are atomics-order noise wander by up to ~lr per step, so after
+        # 50 steps the parameters agree to a few percent of their range while the loss curves agree to 2e-3
+        assert d <= 5e-2 * max(float(p0[k].abs().max()), 1e-2), (k, d)
 
 
 class _FixedRand:
@@ -890,3 +892,51 @@ class _FixedRand:
             self.used = True
             return self.value.clone()
         return _FixedRand.orig(*size, **kw)
+
+
+def test_fused_adam_matches_torch_adam():
+    """tensoir_b200.optim.FusedAdam against torch.optim.Adam over 6 steps: plain, channel-last and odd-sized tensors,
+    two learning rates, the L1 term against autograd of w * |x|.sum(), gradients cleared in place, and the found_inf skip
+    (parameters, moments and step counter untouched)."""
+    from tensoir_b200.optim import FusedAdam
+    g = torch.Generator().manual_seed(3)
+    shapes = [(1, 16, 33, 29), (1, 48, 17, 1), (128, 150), (7,), (4099,)]
+    def make():
+        ps = []
+        for i, sh in enumerate(shapes):
+            t = torch.randn(sh, generator=g).to(DEV)
+            if len(sh) == 4:
+                t = t.contiguous(memory_format=torch.channels_last)
+            ps.append(torch.nn.Parameter(t))
+        return ps
+    g.manual_seed(3); pa = make()
+    g.manual_seed(3); pb = make()
+    l1w = 3e-3
+    oa = torch.optim.Adam([{"params": pa[:2], "lr": 0.02}, {"params": pa[2:], "lr": 1e-3}], betas=(0.9, 0.99))
+    ob = FusedAdam([{"params": pb[:2], "lr": 0.02}, {"params": pb[2:], "lr": 1e-3}], betas=(0.9, 0.99),
+                   l1={pb[0]: l1w})
+    flag = torch.zeros((), device=DEV)
+    ob.found_inf = flag
+    for it in range(6):
+        gs = [torch.randn(p.shape, generator=g).to(DEV) for p in pa]
+        for p, q, gr in zip(pa, pb, gs):
+            gr = gr.contiguous(memory_format=torch.channels_last) if gr.dim() == 4 else gr
+            p.grad = gr.clone() + (l1w * torch.sign(p.detach()) if p is pa[0] else 0)
+            if q.grad is None:
+                q.grad = gr.clone()
+            else:
+                assert float(q.grad.abs().max()) == 0.0            # cleared in place by the previous step
+                q.grad.add_(gr)
+        if it == 3:                                                # a skipped step: nothing but the gradients changes
+            flag.fill_(1.0)
+            before = [q.detach().clone() for q in pb]
+            ob.step()
+            flag.zero_()
+            assert all(torch.equal(x, q.detach()) for x, q in zip(before, pb))
+            for q, gr in zip(pb, gs):
+                q.grad.add_(gr.contiguous(memory_format=torch.channels_last) if gr.dim() == 4 else gr)
+        oa.step()
+        ob.step()
+    for p, q in zip(pa, pb):
+        assert float((p - q).abs().max()) < 2e-6 * max(1.0, float(p.abs().max())), float((p - q).abs().max())
+    assert float(ob.state[pb[0]]["step"]) == 6.0
