@@ -66,6 +66,11 @@ typedef struct TirField {
   int32_t agrid[3];        /* X,Y,Z */
   float a_lo[3];
   float a_inv[3];          /* 1/(hi-lo)*2 as AlphaGridMask.invgridSize */
+  /* world-space bounding box of the alpha-mask CELLS that have a set corner (grown by a guard band): a sample outside it
+   * lies in cells whose 8 corners are all 0, so AlphaGridMask.sample_alpha is exactly 0 there and the marches skip the
+   * lookup (empty-space skipping that cannot change which samples are valid).  occ_lo > occ_hi: no box (test disabled). */
+  float occ_lo[3];
+  float occ_hi[3];
   float density_shift;     /* -10 */
   float distance_scale;    /* 25 */
   float weight_thres;      /* rayMarch_weight_thres 1e-4 */

@@ -27,7 +27,7 @@ class TirField(C.Structure):
         ("dC", C.c_int32), ("aC", C.c_int32), ("grid", C.c_int32 * 3),
         ("aabb_lo", C.c_float * 3), ("aabb_hi", C.c_float * 3), ("inv_aabb", C.c_float * 3),
         ("amask", C.c_void_p), ("acell", C.c_void_p), ("agrid", C.c_int32 * 3),
-        ("a_lo", C.c_float * 3), ("a_inv", C.c_float * 3),
+        ("a_lo", C.c_float * 3), ("a_inv", C.c_float * 3), ("occ_lo", C.c_float * 3), ("occ_hi", C.c_float * 3),
         ("density_shift", C.c_float), ("distance_scale", C.c_float), ("weight_thres", C.c_float),
         ("softplus", C.c_int32),
     ]

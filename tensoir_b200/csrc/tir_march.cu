@@ -192,7 +192,31 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, kBlocksPerSM) march_kerne
 
     int pushed = 0;
     const bool lean = (p.cfg.flags & TIR_MARCH_LEAN_COUNTERS) != 0;
+    // parametric interval of the ray inside the occupied-cell box (slab test); samples outside cannot be valid
+    const bool use_occ = f.amask != nullptr && f.occ_lo[0] <= f.occ_hi[0];
+    float z_in = -3.0e38f, z_out = 3.0e38f;
+    if (use_occ) {
+      const float d3[3] = {dx, dy, dz}, o3[3] = {ox, oy, oz};
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        if (fabsf(d3[a]) > 1e-12f) {
+          const float t0 = (f.occ_lo[a] - o3[a]) / d3[a], t1 = (f.occ_hi[a] - o3[a]) / d3[a];
+          z_in = fmaxf(z_in, fminf(t0, t1)); z_out = fminf(z_out, fmaxf(t0, t1));
+        } else if (o3[a] < f.occ_lo[a] || o3[a] > f.occ_hi[a]) {
+          z_in = 3.0e38f;                       // parallel to the slab and outside it: never inside the box
+        }
+      }
+      // safety margin against the rounding of the slab arithmetic (the per-sample box test below stays exact)
+      const float pad = 1e-3f * (fabsf(z_in) + fabsf(z_out) + 1.f);
+      z_in -= pad; z_out += pad;
+    }
     for (int base = 0; base < N; base += 32) {
+      // lean mode: a whole 32-sample chunk that lies outside the occupied box holds no valid sample, and nobody asked
+      // for the mask counts of its in-aabb samples
+      if (lean && use_occ) {
+        const float za = z_of(base), zb = z_of(min(base + 31, N - 1));
+        if (zb < z_in || za > z_out) continue;
+      }
       // lean mode: a ray whose carried transmittance is exactly 0 cannot change any output any more (see below), and
       // nobody asked for the mask / density counts of its remaining samples, so the rest of the ray is skipped
       if (lean && c_ray == ray && c_T == 0.f) break;
@@ -208,8 +232,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, kBlocksPerSM) march_kerne
         if (!out) {
           valid = true;
           if (f.amask) {
-            c_mask += 1;
-            valid = alpha_mask_positive(f, px, py, pz);
+            c_mask += 1;                       // the reference looks every in-aabb sample up (count parity)
+            // outside the bounding box of the occupied mask cells the trilinear lookup is exactly 0: no byte load
+            const bool in_occ = !use_occ || ((px >= f.occ_lo[0]) & (px <= f.occ_hi[0]) & (py >= f.occ_lo[1]) &
+                                             (py <= f.occ_hi[1]) & (pz >= f.occ_lo[2]) & (pz <= f.occ_hi[2]));
+            valid = in_occ && alpha_mask_positive(f, px, py, pz);
           }
           // normalize_coord (tensorBase:640-641)
           nx = __fsub_rn(__fmul_rn(__fsub_rn(px, f.aabb_lo[0]), f.inv_aabb[0]), 1.f);

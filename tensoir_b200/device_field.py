@@ -95,6 +95,8 @@ class DeviceField:
             s.amask = None
             s.acell = None
             self._mask_key = None
+            for i in range(3):
+                s.occ_lo[i], s.occ_hi[i] = 1.0, -1.0
         else:
             vol = am.alpha_volume
             mkey = _key([vol])
@@ -107,12 +109,28 @@ class DeviceField:
                                                    _lib.dptr(self.acell, torch.uint8), X, Y, Z, _lib.stream_ptr()),
                            "pack_alpha_mask")
                 self._mask_key = mkey
+                # bounding box of the occupied cells (one host read per alpha-mask update, never per step)
+                occ = self.acell.bool()
+                self._occ = None
+                if bool(occ.any()):
+                    ext = []
+                    for axis, n in ((2, X), (1, Y), (0, Z)):                       # x, y, z
+                        hit = occ.any(dim=tuple(d for d in range(3) if d != axis)).nonzero().reshape(-1)
+                        ext.append((int(hit[0]), int(hit[-1]) + 1, n))            # cells [lo, hi) along the axis
+                    alo = am.aabb[0].tolist()
+                    asz = (am.aabb[1] - am.aabb[0]).tolist()
+                    band = 0.02                                                    # guard band in cells
+                    self._occ = ([alo[i] + asz[i] * max(ext[i][0] - band, -1.0) / (ext[i][2] - 1) for i in range(3)],
+                                 [alo[i] + asz[i] * min(ext[i][1] + band, ext[i][2]) / (ext[i][2] - 1) for i in range(3)])
             Z, Y, X = vol.shape[-3:]
             s.amask, s.acell = self.amask.data_ptr(), self.acell.data_ptr()
             s.agrid[0], s.agrid[1], s.agrid[2] = X, Y, Z
             alo, ainv = am._host_geom["lo"], am._host_geom["inv"]
             for i in range(3):
                 s.a_lo[i], s.a_inv[i] = alo[i], ainv[i]
+            occ = getattr(self, "_occ", None)
+            for i in range(3):
+                s.occ_lo[i], s.occ_hi[i] = (occ[0][i], occ[1][i]) if occ is not None else (1.0, -1.0)
         s.density_shift = float(model.density_shift)
         s.distance_scale = float(model.distance_scale)
         s.weight_thres = float(model.rayMarch_weight_thres)

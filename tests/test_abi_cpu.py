@@ -31,7 +31,7 @@ def test_header_symbols_exported(lib):
 
 def test_struct_sizes_match_header(lib):
     from tensoir_b200 import _lib
-    assert (ctypes.sizeof(_lib.TirField), ctypes.sizeof(_lib.TirMlp), ctypes.sizeof(_lib.TirMarchCfg)) == (224, 88, 48)
+    assert (ctypes.sizeof(_lib.TirField), ctypes.sizeof(_lib.TirMlp), ctypes.sizeof(_lib.TirMarchCfg)) == (248, 88, 48)
     assert _lib.APP_SAMPLE_BYTES == 24
     assert ctypes.sizeof(_lib.TirRayMaps) == 64
 
