@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--cpu-rays", type=int, default=1024, help="bounded CPU-baseline sample (primary rays / step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="do not capture the step into a CUDA graph")
+    ap.add_argument("--host-rays", dest="host_rays", action="store_true",
+                    help="end-to-end arm: copy [n,6] rays from the host instead of generating them on the device from ids")
     ap.add_argument("--torch-adam", dest="torch_adam", action="store_true",
                     help="torch.optim.Adam(fused=True) + autograd density_L1 instead of tensoir_b200.optim.FusedAdam")
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
@@ -389,10 +391,34 @@ def measure(a, model, n_lights, rank, world, local, dev, scaling, with_e2e, cloc
            "value": cnt["rays"] / (ms * 1e-3),   # TIR_CNT_RAYS counts every marched ray: primary + secondary
            "last_batch": dev_batches[-1], "n_s": n_s}
     if with_e2e:
-        # ---- end-to-end arm: pinned HOST buffers through the public boundary, loss read back every step
-        for rays, li in pinned[total:total + a.warmup]:
+        # ---- end-to-end arm: pinned HOST buffers through the public boundary, loss read back every step.
+        # Default: the host sends (view, pixel, light) ids - 12 B/ray - and the rays are generated on the device
+        # (ops.generate_rays); --host-rays sends the 28 B/ray the reference's loop indexes from its table.
+        if a.host_rays:
+            e2e_batches = pinned
+            out["e2e_inputs"] = "rays [n,6] fp32 + light_idx from pinned host memory"
+            out["h2d_per_ray"] = 28
+        else:
+            from tensoir_b200.synthetic import training_batch_ids
+            poses_dev = poses.to(dev)
+            slice_ = slice(None) if scaling == "weak" else slice(*shard_batch(a.batch, rank, world))
+            ids = [training_batch_ids(poses.shape[0], a.batch, (it * world + rank) if scaling == "weak" else it,
+                                      n_lights=n_lights) for it in range(2 * total)]
+            ids = [tuple(t[slice_].contiguous().pin_memory() for t in trip) for trip in ids]
+
+            class _Ids:                      # looks like a (rays, light_idx) pair to step(): rays built on the device
+                def __init__(self, trip):
+                    self.trip = trip
+
+                def __iter__(self):
+                    v, p, l = (t.to(dev, non_blocking=True) for t in self.trip)
+                    return iter((ops.generate_rays(poses_dev, v, p), l))
+            e2e_batches = [_Ids(t) for t in ids]
+            out["e2e_inputs"] = "(view, pixel, light) ids from pinned host memory, rays generated on the device"
+            out["h2d_per_ray"] = 12
+        for rays, li in e2e_batches[total:total + a.warmup]:
             step(rays, li)
-        ms_e2e, cnt_e2e, _ = timed_region(pinned[total + a.warmup:2 * total], read_loss=True)
+        ms_e2e, cnt_e2e, _ = timed_region(e2e_batches[total + a.warmup:2 * total], read_loss=True)
         out.update(ms_e2e=ms_e2e, e2e_value=cnt_e2e["rays"] / (ms_e2e * 1e-3))
     out["clocks"] = clocks.stop() if clocks is not None else None
     events1 = (graphed.redone, graphed.recaptures) if graphed is not None else (0, 0)
@@ -502,8 +528,9 @@ def main():
             "secondary_rays_per_s": (cnt["rays"] - per_rank * a.steps * world) / (ms * 1e-3),
             "counters_per_step": {k: v / a.steps for k, v in cnt.items()},
             "e2e": {"value": m["e2e_value"], "unit": UNIT, "ms_per_step": m["ms_e2e"] / a.steps,
-                    # rays + light_idx + the host-drawn per-ray jitter and stratified light directions
-                    "h2d_bytes_per_step": (per_rank * (6 * 4 + 4) + per_rank * 4 + a.envmap_h * a.envmap_w * 3 * 4) * world,
+                    "inputs": m["e2e_inputs"],
+                    # ray inputs + the host-drawn per-ray jitter and stratified light directions
+                    "h2d_bytes_per_step": (per_rank * m["h2d_per_ray"] + per_rank * 4 + a.envmap_h * a.envmap_w * 3 * 4) * world,
                     "d2h_bytes_per_step": 4 * world},
             "counters_note": "mask / density are the queries actually made (TIR_MARCH_LEAN_COUNTERS: the rest of a ray "
                              "whose transmittance is exactly 0 is skipped); rays / app are the reference's counts",

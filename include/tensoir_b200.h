@@ -440,6 +440,12 @@ int tir_adam_step(const TirAdamTensor* table_dev, int32_t n_tensors, const int64
                   int64_t total_chunks, float* state_dev, float beta1, float beta2, float eps,
                   const float* found_inf_dev, int32_t clear_grad, void* stream);
 
+/* On-the-fly ray generation from (view, pixel) ids instead of indexing a [n_views*H*W, 6] host table
+ * (train_tensoIR.py:239-242): directions ((i+0.5-W/2)/f, (j+0.5-H/2)/f, 1) normalised and rotated by c2w[:3,:3], origin
+ * c2w[:3,3] (dataLoader/ray_utils.py:25-43, :67-88).  c2w [n_views,4,4] row-major, pix = j*W + i -> rays [n,6]. */
+int tir_generate_rays(const float* c2w, const int32_t* view_idx, const int32_t* pix_idx, int64_t n, int32_t H, int32_t W,
+                      float focal, float* rays, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -119,3 +119,36 @@ extern "C" int tir_alpha_mask_points(const TirField* field, const float* xyz, in
   alpha_points_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*field, xyz, n, mask);
   return (int)cudaGetLastError();
 }
+
+// ---- on-the-fly ray generation: rays of (view, pixel) ids instead of fancy-indexing a precomputed
+// [n_views*H*W, 6] table on the host (train_tensoIR.py:239-242; get_ray_directions + normalise + get_rays,
+// dataLoader/ray_utils.py:25-43, :67-88, tensoIR_rotation_setting.py:103-114).
+namespace {
+__global__ void generate_rays_kernel(const float* __restrict__ c2w /* [n_views,4,4] row-major */,
+                                     const int32_t* __restrict__ view, const int32_t* __restrict__ pix, int64_t n,
+                                     int32_t H, int32_t W, float focal, float* __restrict__ rays) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const float* M = c2w + (size_t)view[t] * 16;
+  const int p = pix[t];
+  const float i = (float)(p % W) + 0.5f, j = (float)(p / W) + 0.5f;
+  float dx = __fdiv_rn(__fsub_rn(i, 0.5f * (float)W), focal), dy = __fdiv_rn(__fsub_rn(j, 0.5f * (float)H), focal), dz = 1.f;
+  const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), 1.f));
+  dx = __fdiv_rn(dx, nrm); dy = __fdiv_rn(dy, nrm); dz = __fdiv_rn(dz, nrm);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    rays[t * 6 + r] = M[r * 4 + 3];                                                    // origin = c2w[:3, 3]
+    rays[t * 6 + 3 + r] = fmaf(dz, M[r * 4 + 2], fmaf(dy, M[r * 4 + 1], __fmul_rn(dx, M[r * 4 + 0])));   // d @ R^T
+  }
+}
+}  // namespace
+
+extern "C" int tir_generate_rays(const float* c2w, const int32_t* view_idx, const int32_t* pix_idx, int64_t n, int32_t H,
+                                 int32_t W, float focal, float* rays, void* stream) {
+  if (n <= 0) return TIR_OK;
+  if (!c2w || !view_idx || !pix_idx || !rays) return TIR_ERR_NULL;
+  if (H <= 0 || W <= 0 || !(focal > 0.f)) return TIR_ERR_CONFIG;
+  generate_rays_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(c2w, view_idx, pix_idx, n, H, W,
+                                                                                      focal, rays);
+  return (int)cudaGetLastError();
+}

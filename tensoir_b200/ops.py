@@ -277,3 +277,19 @@ class SecondaryStages:
                                         _lib.dptr(self.sc.count, torch.int32), self.sc.capacity, _lib.dptr(self.dr),
                                         self.n_dirs, _lib.dptr(self.li, torch.int32), _lib.dptr(self.ind),
                                         _lib.stream_ptr()), "tir_app_mlp")
+
+
+def generate_rays(c2w, view_idx, pix_idx, H=800, W=800, cam_angle_x=0.6911):
+    """Rays [n,6] of (view, pixel) ids generated on the device: the per-step host work of the train
+    loop (fancy-indexing the all_rays table, train_tensoIR.py:239-242, and copying 24 B/ray) becomes an 8 B/ray id copy.
+    c2w [n_views,4,4] on the device; pix = j*W + i."""
+    import math
+    lib = _lib.load()
+    c2w = _f32c(c2w.reshape(-1, 4, 4))
+    v, p = _i32c(view_idx), _i32c(pix_idx)
+    n = v.shape[0]
+    rays = torch.empty(n, 6, device=c2w.device)
+    focal = 0.5 * W / math.tan(0.5 * cam_angle_x)
+    _lib.check(lib.tir_generate_rays(_lib.dptr(c2w), _lib.dptr(v, torch.int32), _lib.dptr(p, torch.int32), n, H, W,
+                                     float(focal), _lib.dptr(rays), _lib.stream_ptr()), "tir_generate_rays")
+    return rays

@@ -148,6 +148,17 @@ def training_batch(poses: torch.Tensor, batch: int, step: int, H: int = 800, W: 
     return rays, light
 
 
+def training_batch_ids(n_views: int, batch: int, step: int, H: int = 800, W: int = 800, n_lights: int = 1,
+                       seed: int = SEED):
+    """The (view, pixel, light) ids of :func:`training_batch` without building the rays (same generator sequence):
+    what the host sends per step when the rays are generated on the device (ops.generate_rays)."""
+    g = torch.Generator().manual_seed(seed + 1000003 * step)
+    view = torch.randint(0, n_views, (batch,), generator=g)
+    pix = torch.randint(0, H * W, (batch,), generator=g)
+    light = torch.randint(0, n_lights, (batch, 1), generator=g, dtype=torch.int32)
+    return view.to(torch.int32), pix.to(torch.int32), light
+
+
 def make_lego_model(grid: int, device, *, lights=("000",), general=False, mask_res=None, seed: int = SEED,
                     envmap=(16, 32)):
     """The benchmark field: TensorVMSplit at ``grid``^3 on aabb +-1.5 with the lego box density installed,

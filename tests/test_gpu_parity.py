@@ -940,3 +940,22 @@ def test_fused_adam_matches_torch_adam():
     for p, q in zip(pa, pb):
         assert float((p - q).abs().max()) < 2e-6 * max(1.0, float(p.abs().max())), float((p - q).abs().max())
     assert float(ob.state[pb[0]]["step"]) == 6.0
+
+
+def test_device_ray_generation_matches_host_rays():
+    """tir_generate_rays (rays of (view, pixel) ids on the device) against the host construction the datasets use
+    (get_ray_directions + normalise + get_rays, restated in tensoir_b200.synthetic.pixel_rays)."""
+    from tensoir_b200 import ops
+    from tensoir_b200.synthetic import hemisphere_poses, pixel_rays
+    poses = hemisphere_poses(100)
+    g = torch.Generator().manual_seed(1)
+    view = torch.randint(0, 100, (5000,), generator=g, dtype=torch.int32)
+    pix = torch.randint(0, 800 * 800, (5000,), generator=g, dtype=torch.int32)
+    want = torch.empty(5000, 6)
+    for v in view.unique().tolist():
+        m = view == v
+        want[m] = pixel_rays(poses[v], pix[m].long())
+    got = ops.generate_rays(poses.to(DEV), view.to(DEV), pix.to(DEV)).cpu()
+    assert torch.equal(got[:, :3], want[:, :3])
+    assert float((got[:, 3:] - want[:, 3:]).abs().max()) < 3e-7
+    assert float((got[:, 3:].norm(dim=-1) - 1).abs().max()) < 1e-6
