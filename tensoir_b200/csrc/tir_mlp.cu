@@ -149,13 +149,20 @@ __device__ __forceinline__ void warp_gemm(float (&acc)[MT][NTL][4], const __nv_b
   }
 }
 
-// Write columns [0, ncol) of the activation tile (hi + lo) to a row-major fp32 global array.
+// Write columns [0, ncol) of the activation tile (hi + lo) to a row-major fp32 global array (ncol even): a warp writes
+// one row at a time as float2 (coalesced 256-byte segments, no integer division).
 __device__ __forceinline__ void dump_tile(const __nv_bfloat16* ah, const __nv_bfloat16* al, float* dst, int ncol,
                                           int64_t base, int64_t total, int tid) {
-  for (int i = tid; i < M * ncol; i += NT) {
-    const int row = i / ncol, col = i - row * ncol;
-    if (base + row < total)
-      dst[(base + row) * ncol + col] = __bfloat162float(ah[row * SA + col]) + __bfloat162float(al[row * SA + col]);
+  const int lane = tid & 31, warp = tid >> 5;
+  for (int row = warp; row < M; row += NT / 32) {
+    if (base + row >= total) break;
+    float* d = dst + (base + row) * ncol;
+    for (int c = 2 * lane; c < ncol; c += 64) {
+      const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(ah + row * SA + c);
+      const __nv_bfloat162 l = *reinterpret_cast<const __nv_bfloat162*>(al + row * SA + c);
+      *reinterpret_cast<float2*>(d + c) = make_float2(__bfloat162float(h.x) + __bfloat162float(l.x),
+                                                     __bfloat162float(h.y) + __bfloat162float(l.y));
+    }
   }
 }
 

@@ -1,7 +1,7 @@
 // Blackwell-native appearance MLP (sm_100a): the secondary-ray appearance head of compute_radiance
 // (models/relight_utils.py:803-834) = compute_appfeature (tensoRF_rotated_lights.py:197-224) + MLPRender_Fea
-// (tensorBase_rotated_lights.py:122-146) on the compacted appearance-sample list, with the two 128-wide layers on the
-// 5th-generation tensor cores:
+// (tensorBase_rotated_lights.py:122-146) on the compacted appearance-sample list, with basis_mat and the two 128-wide
+// layers on the 5th-generation tensor cores:
 //
 //   * tcgen05.mma (kind::f16, M = 128 samples x N = 128 units x K = 16) issued by ONE thread; accumulator in TMEM;
 //   * the A operand (MLP input / hidden activations, error-compensated split BF16: hi + lo) lives in TMEM as well
@@ -10,11 +10,13 @@
 //     the canonical no-swizzle K-major layout for the whole persistent CTA;
 //   * every product is hi*hi + hi*lo + lo*hi accumulated in fp32 (the dropped lo*lo term is 2^-16 relative);
 //   * two warpgroups of 128 threads (thread = sample row = TMEM lane) ping-pong through ONE issuer thread: while one
-//     group's MMAs run or its accumulator drains, the other gathers (216 x LDG.128 per sample, plane*line*light ->
-//     basis_mat in exact fp32 on the CUDA cores) — the L2-latency-bound gather overlaps the tensor work;
+//     group's MMAs run or its accumulator drains, the other gathers (108 x 256-bit loads per sample; the products
+//     plane*line*light go straight into TMEM as the A operand of the basis_mat GEMM) — the L2-latency-bound gather
+//     overlaps the tensor work;
+//   * three MMA stages per 128-sample tile: basis_mat (K = 144, N = 32), layer 0 (K = 160, N = 128), layer 1 (K = 128);
 //   * TMEM map (512 columns): P0 [0,160) / P1 [160,320) = A operand of group 0 / 1 (hi | lo halves), Q [320,448) = the
 //     shared fp32 accumulator, handed from group to group with mbarriers.
-//   The last layer (128 -> 3/4) and basis_mat (144 -> 27) are <= 10 % of the FLOPs and run in fp32 on the CUDA cores.
+//   The last layer (128 -> 3/4, < 1 % of the FLOPs) runs in fp32 on the CUDA cores.
 //
 // The descriptor / TMEM-operand conventions are the ones experiments/umma_probe validated on a B200
 // (gpurun_out/r2_c1/umma_probe.txt: SS and TS forms exact to 1e-6, 77 cycles per 128x128x16 MMA).

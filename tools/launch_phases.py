@@ -12,8 +12,9 @@ import csv
 import re
 import sys
 
-OWN = ("march_kernel", "app_mlp_kernel", "app_products", "composite_", "shade_", "density_", "valid_samples",
-       "pack_", "unpack_")
+OWN = ("march_kernel", "app_mlp", "app_products", "composite_", "shade_", "density_", "valid_samples", "pack_",
+       "unpack_", "heads_", "primary_", "scan_counts", "app_fill", "jitter_points", "epilogue_", "tail_", "adam_",
+       "hits_prepare", "generate_rays")
 
 
 def load(path):
