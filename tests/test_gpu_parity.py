@@ -206,7 +206,7 @@ def test_boundary_train_step_grads(golden_rotated):
             + 0.001 * got["albedo_smoothness_loss"] + 0.001 * got["roughness_smoothness_loss"])
     loss.backward()
     close(loss, fx["renderer_train_loss"], TOL, "loss")
-    n = 0
+    n, worst = 0, {}
     for k, p in m.named_parameters():
         w = fx["renderer_train_grads"][k]
         if w is None:
@@ -215,9 +215,11 @@ def test_boundary_train_step_grads(golden_rotated):
         g = p.grad.detach().cpu()
         scale = float(w.abs().max()) + 1e-12
         err = float((g - w).abs().max()) / scale
-        assert err < 2e-3, (k, err)
+        worst[k] = err
         n += 1
     assert n >= 20
+    bad = {k: v for k, v in worst.items() if v > 5e-4}
+    assert not bad, (bad, max(worst.values()))
 
 
 def test_general_and_init_models(golden_general, golden_init):
@@ -497,6 +499,44 @@ def test_fused_shade_kernel_vs_reference_math(golden_rotated):
     for name, a, b in zip(("normal", "albedo", "rough", "fresnel", "direct"), leaves, leaves_ref):
         scale = float(b.grad.abs().max()) + 1e-12
         assert float((a.grad - b.grad).abs().max()) / scale < 5e-4, name
+
+
+def test_fused_shade_kernel_full_roughness_range_vs_fp64(golden_rotated):
+    """Roughness over the model's whole range [0.09, 0.99] (primary.py: brdf[..., 3] * 0.9 + 0.09).  Below ~0.25 GGX's
+    nom0 = NoH^2 (alpha^2 - 1) + 1 cancels catastrophically near the specular peak, so two fp32 evaluation orders differ
+    by ~1e-3 and comparing them with each other says little; both are compared with the SAME expressions in fp64 instead:
+    the kernel is at least as close to the exact value as the reference's fp32 torch evaluation (x2 + 1e-6 slack)."""
+    from tensoir_b200.shade import shade
+    f = oracle_field(golden_rotated)
+    g = torch.Generator().manual_seed(9)
+    bs, nl = 64, 512
+    nrm = torch.nn.functional.normalize(torch.randn(bs, 3, generator=g), dim=-1)
+    alb, fres = torch.rand(bs, 3, generator=g), torch.full((bs, 3), 0.04)
+    rough = (torch.rand(bs, 1, generator=g) * 0.9 + 0.09).repeat(1, 3)
+    rough[:8] = 0.09                                                     # the lower end explicitly
+    view = torch.nn.functional.normalize(torch.randn(bs, 3, generator=g), dim=-1)
+    direct = torch.rand(1, nl, 3, generator=g) * 2
+    vis, ind = torch.rand(bs, nl, 1, generator=g), torch.rand(bs, nl, 3, generator=g) * 0.3
+    li = torch.zeros(bs, 1, dtype=torch.long)
+    torch.manual_seed(1)
+    dirs = O.gen_light_incident_dirs(f, 'stratified_sampling')
+    w = O.generate_envir_map_dir(16, 32)[0]
+
+    def ref(dt):
+        n_, a_, r_, f_, d_, v_, dr, ww, vs, ii = (t.to(DEV, dt) for t in (nrm, alb, rough, fres, direct, view, dirs, w,
+                                                                         vis, ind))
+        surf2l = dr[None].expand(bs, -1, -1)
+        cos = torch.clamp(torch.einsum("ijk,ik->ij", surf2l, n_), min=0.0)
+        brdf = a_.unsqueeze(1) / torch.pi + O.ggx_specular(n_, v_, surf2l, r_, f_)
+        light = vs * d_[0][None] + ii
+        return torch.sum(brdf * light * cos[:, :, None] * ww[None, :, None], dim=1)
+    exact, ref32 = ref(torch.float64), ref(torch.float32)
+    got = shade(*(t.to(DEV) for t in (nrm, alb, rough, fres, direct, view, li, dirs, w, vis, ind)))
+    scale = exact.abs().clamp_min(1e-3)
+    e_ours = float(((got.double() - exact).abs() / scale).max())
+    e_ref = float(((ref32.double() - exact).abs() / scale).max())
+    assert e_ours <= 2 * e_ref + 1e-6, (e_ours, e_ref)
+    assert e_ours < 5e-3, e_ours
 
 
 def test_relight_chunk(golden_rotated):
