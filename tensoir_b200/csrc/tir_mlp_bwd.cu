@@ -365,8 +365,8 @@ struct WgradSmem {
   float colsum[8 * HID];
 };
 
-constexpr int P_W = 12;     // CTAs (row slices) per head for each of the two big weight gradients
-constexpr int P_S = 8;      // CTAs per head for the small ones (gW2, gb2, g basis_mat)
+constexpr int P_W = 14;     // CTAs (row slices) per head for each of the two big weight gradients
+constexpr int P_S = 9;      // CTAs per head for the small ones (gW2, gb2, g basis_mat)
 constexpr int CTAS_PER_JOB = 2 * P_W + P_S;
 
 // acc[NT8][4] += A^T B over one 64-row tile: rows m0..m0+15 of the gradient (A columns), columns n0.. (B columns).

@@ -96,38 +96,42 @@ __global__ void app_products_kernel(TirField f, const float* __restrict__ xn, in
   }
 }
 
+// One thread per (point, orientation, 4-channel chunk): the appearance list is short (~15 k points per step), so the work
+// is spread over C/4 = 12x more threads than a per-(point, orientation) loop, and consecutive threads hit consecutive
+// 16-byte chunks of the same texel (coalesced loads and atomics).
 template <int C>
 __global__ void app_products_bwd_kernel(TirField f, const float* __restrict__ xn, int64_t n_cap,
                                         const int64_t* __restrict__ n_dev, const float* __restrict__ gout,
                                         const float* __restrict__ gout1, const float* __restrict__ gout2, GradPtrs g) {
+  constexpr int Q = C / 4;
   const int64_t n = list_rows(n_cap, n_dev);
-  const int64_t total = n * 3;
+  const int64_t total = n * 3 * Q;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i = t / 3;
-    const int k = (int)(t - i * 3);
+    const int64_t pk = t / Q;
+    const int c = (int)(t - pk * Q) * 4;
+    const int64_t i = pk / 3;
+    const int k = (int)(pk - i * 3);
     const float x[3] = {xn[i * 3], xn[i * 3 + 1], xn[i * 3 + 2]};
     const int m0 = kMat0[k], m1 = kMat1[k], v = kVec[k];
     const Bilinear b = bilinear_setup(x[m0], x[m1], f.grid[m0], f.grid[m1]);
     const Linear1 l = linear_setup(x[v], f.grid[v]);
     const float* P = f.aplane[k];
     const float* L = f.aline[k];
-    const int64_t go_off = i * (3 * C) + k * C;
-    for (int c = 0; c < C; c += 4) {
-      float4 gv = *reinterpret_cast<const float4*>(gout + go_off + c);
-      if (gout1) gv = f4_add(gv, *reinterpret_cast<const float4*>(gout1 + go_off + c));   // heads sharing the points
-      if (gout2) gv = f4_add(gv, *reinterpret_cast<const float4*>(gout2 + go_off + c));
-      const float4 pv = bilerp4(ldg4(P + (size_t)b.o00 * C + c), ldg4(P + (size_t)b.o01 * C + c),
-                                ldg4(P + (size_t)b.o10 * C + c), ldg4(P + (size_t)b.o11 * C + c), b);
-      const float4 lv = lerp4(ldg4(L + (size_t)l.o0 * C + c), ldg4(L + (size_t)l.o1 * C + c), l);
-      const float4 gp = f4_mul(gv, lv);   // d/d plane value
-      const float4 gl = f4_mul(gv, pv);   // d/d line value
-      if (b.nw != 0.f) red4(g.plane[k] + (size_t)b.o00 * C + c, f4_scale(gp, b.nw));
-      if (b.ne != 0.f) red4(g.plane[k] + (size_t)b.o01 * C + c, f4_scale(gp, b.ne));
-      if (b.sw != 0.f) red4(g.plane[k] + (size_t)b.o10 * C + c, f4_scale(gp, b.sw));
-      if (b.se != 0.f) red4(g.plane[k] + (size_t)b.o11 * C + c, f4_scale(gp, b.se));
-      if (l.w0 != 0.f) red4(g.line[k] + (size_t)l.o0 * C + c, f4_scale(gl, l.w0));
-      if (l.w1 != 0.f) red4(g.line[k] + (size_t)l.o1 * C + c, f4_scale(gl, l.w1));
-    }
+    const int64_t go_off = i * (3 * C) + k * C + c;
+    float4 gv = *reinterpret_cast<const float4*>(gout + go_off);
+    if (gout1) gv = f4_add(gv, *reinterpret_cast<const float4*>(gout1 + go_off));   // heads sharing the points
+    if (gout2) gv = f4_add(gv, *reinterpret_cast<const float4*>(gout2 + go_off));
+    const float4 pv = bilerp4(ldg4(P + (size_t)b.o00 * C + c), ldg4(P + (size_t)b.o01 * C + c),
+                              ldg4(P + (size_t)b.o10 * C + c), ldg4(P + (size_t)b.o11 * C + c), b);
+    const float4 lv = lerp4(ldg4(L + (size_t)l.o0 * C + c), ldg4(L + (size_t)l.o1 * C + c), l);
+    const float4 gp = f4_mul(gv, lv);   // d/d plane value
+    const float4 gl = f4_mul(gv, pv);   // d/d line value
+    if (b.nw != 0.f) red4(g.plane[k] + (size_t)b.o00 * C + c, f4_scale(gp, b.nw));
+    if (b.ne != 0.f) red4(g.plane[k] + (size_t)b.o01 * C + c, f4_scale(gp, b.ne));
+    if (b.sw != 0.f) red4(g.plane[k] + (size_t)b.o10 * C + c, f4_scale(gp, b.sw));
+    if (b.se != 0.f) red4(g.plane[k] + (size_t)b.o11 * C + c, f4_scale(gp, b.se));
+    if (l.w0 != 0.f) red4(g.line[k] + (size_t)l.o0 * C + c, f4_scale(gl, l.w0));
+    if (l.w1 != 0.f) red4(g.line[k] + (size_t)l.o1 * C + c, f4_scale(gl, l.w1));
   }
 }
 
@@ -209,14 +213,18 @@ __global__ void density_grad_kernel(TirField f, const float* __restrict__ xn, in
   }
 }
 
+// one thread per (point, orientation, 4-channel chunk), like app_products_bwd_kernel
 template <int C>
 __global__ void density_grad_bwd_kernel(TirField f, const float* __restrict__ xn, int64_t n_cap,
                                         const int64_t* __restrict__ n_dev, const float* __restrict__ g_feat,
                                         const float* __restrict__ g_dfdx, GradPtrs g) {
-  const int64_t total = list_rows(n_cap, n_dev) * 3;
+  constexpr int Q = C / 4;
+  const int64_t total = list_rows(n_cap, n_dev) * 3 * Q;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i = t / 3;
-    const int k = (int)(t - i * 3);
+    const int64_t pk = t / Q;
+    const int c = (int)(t - pk * Q) * 4;
+    const int64_t i = pk / 3;
+    const int k = (int)(pk - i * 3);
     const float x[3] = {xn[i * 3], xn[i * 3 + 1], xn[i * 3 + 2]};
     const int m0 = kMat0[k], m1 = kMat1[k], v = kVec[k];
     const int W = f.grid[m0], H = f.grid[m1], D = f.grid[v];
@@ -232,25 +240,22 @@ __global__ void density_grad_bwd_kernel(TirField f, const float* __restrict__ xn
     const float a_sw = gf * b.sw + g0 * b.dx_sw + g1 * b.dy_sw, a_se = gf * b.se + g0 * b.dx_se + g1 * b.dy_se;
     const float* P = f.dplane[k];
     const float* L = f.dline[k];
-#pragma unroll
-    for (int c = 0; c < C; c += 4) {
-      const float4 a = ldg4(P + (size_t)b.o00 * C + c), bb = ldg4(P + (size_t)b.o01 * C + c),
-                   cc = ldg4(P + (size_t)b.o10 * C + c), d = ldg4(P + (size_t)b.o11 * C + c);
-      const float4 l0 = ldg4(L + (size_t)l.o0 * C + c), l1 = ldg4(L + (size_t)l.o1 * C + c);
-      const float4 pv = f4_comb4(a, bb, cc, d, b.nw, b.ne, b.sw, b.se);
-      const float4 px = f4_comb4(a, bb, cc, d, b.dx_nw, b.dx_ne, b.dx_sw, b.dx_se);
-      const float4 py = f4_comb4(a, bb, cc, d, b.dy_nw, b.dy_ne, b.dy_sw, b.dy_se);
-      const float4 lv = f4_add(f4_scale(l0, l.w0), f4_scale(l1, l.w1));
-      const float4 dl = f4_sub(l1, l0);
-      red4(g.plane[k] + (size_t)b.o00 * C + c, f4_add(f4_scale(lv, a_nw), f4_scale(dl, gv * b.nw)));
-      red4(g.plane[k] + (size_t)b.o01 * C + c, f4_add(f4_scale(lv, a_ne), f4_scale(dl, gv * b.ne)));
-      red4(g.plane[k] + (size_t)b.o10 * C + c, f4_add(f4_scale(lv, a_sw), f4_scale(dl, gv * b.sw)));
-      red4(g.plane[k] + (size_t)b.o11 * C + c, f4_add(f4_scale(lv, a_se), f4_scale(dl, gv * b.se)));
-      // coefficient of L_u: pv*(gf*wl_u -/+ gv) + wl_u*(g0*px + g1*py)
-      const float4 q = f4_add(f4_scale(px, g0), f4_scale(py, g1));
-      red4(g.line[k] + (size_t)l.o0 * C + c, f4_add(f4_scale(pv, gf * l.w0 - gv), f4_scale(q, l.w0)));
-      red4(g.line[k] + (size_t)l.o1 * C + c, f4_add(f4_scale(pv, gf * l.w1 + gv), f4_scale(q, l.w1)));
-    }
+    const float4 a = ldg4(P + (size_t)b.o00 * C + c), bb = ldg4(P + (size_t)b.o01 * C + c),
+                 cc = ldg4(P + (size_t)b.o10 * C + c), d = ldg4(P + (size_t)b.o11 * C + c);
+    const float4 l0 = ldg4(L + (size_t)l.o0 * C + c), l1 = ldg4(L + (size_t)l.o1 * C + c);
+    const float4 pv = f4_comb4(a, bb, cc, d, b.nw, b.ne, b.sw, b.se);
+    const float4 px = f4_comb4(a, bb, cc, d, b.dx_nw, b.dx_ne, b.dx_sw, b.dx_se);
+    const float4 py = f4_comb4(a, bb, cc, d, b.dy_nw, b.dy_ne, b.dy_sw, b.dy_se);
+    const float4 lv = f4_add(f4_scale(l0, l.w0), f4_scale(l1, l.w1));
+    const float4 dl = f4_sub(l1, l0);
+    red4(g.plane[k] + (size_t)b.o00 * C + c, f4_add(f4_scale(lv, a_nw), f4_scale(dl, gv * b.nw)));
+    red4(g.plane[k] + (size_t)b.o01 * C + c, f4_add(f4_scale(lv, a_ne), f4_scale(dl, gv * b.ne)));
+    red4(g.plane[k] + (size_t)b.o10 * C + c, f4_add(f4_scale(lv, a_sw), f4_scale(dl, gv * b.sw)));
+    red4(g.plane[k] + (size_t)b.o11 * C + c, f4_add(f4_scale(lv, a_se), f4_scale(dl, gv * b.se)));
+    // coefficient of L_u: pv*(gf*wl_u -/+ gv) + wl_u*(g0*px + g1*py)
+    const float4 q = f4_add(f4_scale(px, g0), f4_scale(py, g1));
+    red4(g.line[k] + (size_t)l.o0 * C + c, f4_add(f4_scale(pv, gf * l.w0 - gv), f4_scale(q, l.w0)));
+    red4(g.line[k] + (size_t)l.o1 * C + c, f4_add(f4_scale(pv, gf * l.w1 + gv), f4_scale(q, l.w1)));
   }
 }
 
@@ -408,7 +413,7 @@ int launch_app_products_bwd(const TirField& f, const float* xn, int64_t n, const
                             const float* g1, const float* g2, const GradPtrs& g, cudaStream_t stream) {
   if (n <= 0) return TIR_OK;
   if (f.aC != 48) return TIR_ERR_SHAPE;
-  app_products_bwd_kernel<48><<<blocks_for(n * 3, 128), 128, 0, stream>>>(f, xn, n, n_dev, g0, g1, g2, g);
+  app_products_bwd_kernel<48><<<blocks_for(n * 3 * 12, 128), 128, 0, stream>>>(f, xn, n, n_dev, g0, g1, g2, g);
   return (int)cudaGetLastError();
 }
 int launch_density_grad(const TirField& f, const float* xn, int64_t n, const int64_t* n_dev, float* feature,
@@ -422,7 +427,7 @@ int launch_density_grad_bwd(const TirField& f, const float* xn, int64_t n, const
                             const float* g_dfdx, const GradPtrs& g, cudaStream_t stream) {
   if (n <= 0) return TIR_OK;
   if (f.dC != 16) return TIR_ERR_SHAPE;
-  density_grad_bwd_kernel<16><<<blocks_for(n * 3, 128), 128, 0, stream>>>(f, xn, n, n_dev, g_feature, g_dfdx, g);
+  density_grad_bwd_kernel<16><<<blocks_for(n * 3 * 4, 128), 128, 0, stream>>>(f, xn, n, n_dev, g_feature, g_dfdx, g);
   return (int)cudaGetLastError();
 }
 }  // namespace tir
@@ -442,7 +447,7 @@ extern "C" int tir_vm_app_products_bwd(const TirField* field, const float* xn, i
   if (field->aC != 48) return TIR_ERR_SHAPE;
   GradPtrs g;
   for (int k = 0; k < 3; ++k) { g.plane[k] = g_plane[k]; g.line[k] = g_line[k]; }
-  app_products_bwd_kernel<48><<<blocks_for(n * 3, 128), 128, 0, (cudaStream_t)stream>>>(*field, xn, n, nullptr, g_out,
+  app_products_bwd_kernel<48><<<blocks_for(n * 3 * 12, 128), 128, 0, (cudaStream_t)stream>>>(*field, xn, n, nullptr, g_out,
                                                                                        nullptr, nullptr, g);
   return (int)cudaGetLastError();
 }
@@ -475,7 +480,7 @@ extern "C" int tir_vm_density_grad_bwd(const TirField* field, const float* xn, i
   if (field->dC != 16) return TIR_ERR_SHAPE;
   GradPtrs g;
   for (int k = 0; k < 3; ++k) { g.plane[k] = g_plane[k]; g.line[k] = g_line[k]; }
-  density_grad_bwd_kernel<16><<<blocks_for(n * 3, 128), 128, 0, (cudaStream_t)stream>>>(*field, xn, n, nullptr,
+  density_grad_bwd_kernel<16><<<blocks_for(n * 3 * 4, 128), 128, 0, (cudaStream_t)stream>>>(*field, xn, n, nullptr,
                                                                                        g_feature, g_dfdx, g);
   return (int)cudaGetLastError();
 }
