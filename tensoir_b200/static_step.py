@@ -44,7 +44,7 @@ def lr_tensors(param_groups, device):
 
 
 class StaticTrainStep:
-    LISTS = ("cap_valid", "cap_app", "cap_hit")
+    LISTS = ("cap_valid", "cap_app")      # surface hits are not a list any more (relight_utils.render_hits)
 
     def __init__(self, model, optimizer, n_rays, n_samples, args, loss_fn, *, sample_method="stratified_sampling",
                  cap_valid=None, cap_app=None, grad_bucket=None, device=None, grow_at=0.8, headroom=1.5, lag=2):
@@ -58,11 +58,11 @@ class StaticTrainStep:
         self.light_idx = torch.zeros(n_rays, 1, dtype=torch.int32, device=dev)
         n_dirs = model.envmap_h * model.envmap_w
         self.static = {"cap_valid": int(cap_valid or 256 * n_rays), "cap_app": int(cap_app or 16 * n_rays),
-                       "cap_hit": self.n_rays, "sec_per_slot": 4,
+                       "sec_per_slot": 4,
                        "jitter": torch.zeros(n_rays, 1, device=dev),
                        "dirs": torch.zeros(n_dirs, 3, device=dev),
-                       # real list lengths of the last step: valid samples, appearance samples, surface hits,
-                       # secondary appearance samples (device side; the host reads them one step late)
+                       # real list lengths of the last step: valid samples, appearance samples, (unused), secondary
+                       # appearance samples (device side; the host reads them `lag` steps late)
                        "stats": torch.zeros(4, dtype=torch.int64, device=dev),
                        "overflow_step": torch.zeros((), dtype=torch.int64, device=dev),
                        "overflow": torch.zeros((), dtype=torch.int64, device=dev)}
@@ -91,19 +91,17 @@ class StaticTrainStep:
         from . import primary
         headroom = float(headroom or self.headroom)
         self.model.__dict__.pop("_tir_static", None)
-        nv = na = nh = 0
+        nv = na = 0
         for rays, _ in batches:
             m = primary.march(self.model, rays.to(self.dev).float(), True, self.n_samples)
             nv = max(nv, int(m["xn"].shape[0]))
             na = max(na, int((m["weight"] > self.model.rayMarch_weight_thres).sum().item()))
-            nh = max(nh, int((m["acc"] > 0.5).sum().item()))
-        self._set_caps(int(headroom * nv) + 4096, int(headroom * na) + 1024, int(headroom * nh) + 64)
-        return self.static["cap_valid"], self.static["cap_app"], self.static["cap_hit"]
+        self._set_caps(int(headroom * nv) + 4096, int(headroom * na) + 1024)
+        return self.capacities()
 
-    def _set_caps(self, cap_valid, cap_app, cap_hit):
+    def _set_caps(self, cap_valid, cap_app, *_unused):
         self.static["cap_valid"] = int(min(cap_valid, self.n_rays * max(self.n_samples, 1)))
         self.static["cap_app"] = int(min(cap_app, self.static["cap_valid"]))
-        self.static["cap_hit"] = int(min(self.n_rays, cap_hit))
 
     def capacities(self):
         return tuple(self.static[k] for k in self.LISTS)
@@ -201,15 +199,15 @@ class StaticTrainStep:
     def _inspect(self, slot):
         """Look at a finished step: -> (overflowed, grow) with grow = new capacities or None."""
         slot["event"].synchronize()
-        n_valid, n_app, n_hit, n_sec, over = (int(v) for v in slot["stats"].tolist())
+        n_valid, n_app, _, n_sec, over = (int(v) for v in slot["stats"].tolist())
         slot["event"] = None
         caps = self.capacities()
-        seen = (n_valid, n_app, n_hit)
-        old = getattr(self, "_seen", (0, 0, 0, 0))
-        self._seen = tuple(max(a, b) for a, b in zip(old, (n_valid, n_app, n_hit, n_sec)))
+        seen = (n_valid, n_app)
+        old = getattr(self, "_seen", (0, 0, 0))
+        self._seen = tuple(max(a, b) for a, b in zip(old, (n_valid, n_app, n_sec)))
         want = list(caps)
-        for i in range(3):
-            if i < 2 and seen[i] > self.grow_at * caps[i]:      # (the surface hits are not a list any more)
+        for i in range(2):
+            if seen[i] > self.grow_at * caps[i]:
                 want[i] = int(self.headroom * seen[i]) + 64
         slots = self.n_rays * self.static["dirs"].shape[0]
         sec_cap = max(1 << 16, self.static["sec_per_slot"] * slots)
@@ -279,7 +277,7 @@ class StaticTrainStep:
         if seen is None:
             return self.capacities()
         caps = self.capacities()
-        want = tuple(max(c, int(factor * v) + 64) for c, v in zip(caps, seen[:3]))
+        want = tuple(max(c, int(factor * v) + 64) for c, v in zip(caps, seen[:2]))
         self._set_caps(*want)
         if self.capacities() != caps:
             new = self.capacities()

@@ -316,7 +316,7 @@ def test_static_capacity_mode_matches_dynamic(golden_rotated):
         if static:
             jit = torch.rand(64, 1)
             dirs = m.gen_light_incident_dirs(method='stratified_sampling')
-            m.__dict__["_tir_static"] = {"cap_valid": 64 * 60, "cap_app": 1024, "cap_hit": 60, "jitter": jit.to(DEV),
+            m.__dict__["_tir_static"] = {"cap_valid": 64 * 60, "cap_app": 1024, "jitter": jit.to(DEV),
                                          "dirs": dirs.to(DEV), "overflow": torch.zeros((), dtype=torch.int64, device=DEV),
                                          "stats": torch.zeros(4, dtype=torch.int64, device=DEV),
                                          "overflow_step": torch.zeros((), dtype=torch.int64, device=DEV)}
