@@ -162,9 +162,9 @@ class _PrimaryRelight(torch.autograd.Function):
             _lib.check(cd.tir_primary_march(C.byref(f), _lib.dptr(rays), n_rays, C.byref(cfg), C.byref(w), cptr, stream),
                        "tir_primary_march")
             if st is not None:
-                from .primary import note_count
-                note_count(st, 0, ws.t["status"][0], ws.cap_valid)
-                note_count(st, 1, ws.t["status"][1], ws.cap_app)
+                # shape-static mode: the kernels already left the real list lengths and the overflow flag on the device
+                st["stats"][0:2].copy_(ws.t["status"][0:2])
+                st["overflow_step"].add_(ws.t["status"][2])
                 break
             n_valid, n_app, _, _ = ws.t["status"].tolist()          # the one host read of the eager forward
             if n_valid <= ws.cap_valid and n_app <= ws.cap_app:
@@ -249,19 +249,30 @@ class _PrimaryRelight(torch.autograd.Function):
         for k in range(3):
             gr.dplane[k], gr.dline[k] = bufs[k].data_ptr(), bufs[3 + k].data_ptr()
             gr.aplane[k], gr.aline[k] = bufs[6 + k].data_ptr(), bufs[9 + k].data_ptr()
-        g_basis = torch.zeros_like(model.basis_mat.weight)
+        inplace = model.__dict__.get("_tir_grad_inplace", True)
+
+        def target(p):
+            """(buffer the kernels accumulate into, what autograd gets): the parameter's own .grad when it is a plain
+            fp32 tensor of the same layout (then autograd gets None: no zero-fill, no AccumulateGrad add), else zeros."""
+            g = p.grad
+            if inplace and g is not None and g.dtype == torch.float32 and g.shape == p.shape and g.is_contiguous() \
+                    and p.is_contiguous():
+                return g, None
+            z = torch.zeros_like(p)
+            return z, z
+        g_basis, r_basis = target(model.basis_mat.weight)
         gr.basis = g_basis.data_ptr()
         ll = getattr(model, "light_line", None)
-        g_light = torch.zeros_like(ll.weight) if ll is not None else None
+        g_light, r_light = target(ll.weight) if ll is not None else (None, None)
         gr.light_line = None if g_light is None else g_light.data_ptr()
         mod_grads = {}
         for j, head in enumerate(ctx.heads):
             if head not in mod_grads:
                 m = getattr(model, head).mlp
-                mod_grads[head] = [torch.zeros_like(t) for t in (m[0].weight, m[0].bias, m[2].weight, m[2].bias,
-                                                                 m[4].weight, m[4].bias)]
+                mod_grads[head] = [target(t) for t in (m[0].weight, m[0].bias, m[2].weight, m[2].bias, m[4].weight,
+                                                       m[4].bias)]
             g = mod_grads[head]
-            gr.w0[j], gr.b0[j], gr.w1[j], gr.b1[j], gr.w2[j], gr.b2[j] = [t.data_ptr() for t in g]
+            gr.w0[j], gr.b0[j], gr.w1[j], gr.b1[j], gr.w2[j], gr.b2[j] = [t[0].data_ptr() for t in g]
         white_bg, bg_flag, n_samples, is_train = ctx.cfg_args
         _lib.check(cd.tir_primary_backward(C.byref(f), jobs, n_jobs, kind, _lib.dptr(rays), _lib.dptr(li, torch.int32),
                                            n_rays, C.byref(w), C.byref(b), float(model.fixed_fresnel), int(bg_flag),
@@ -273,9 +284,9 @@ class _PrimaryRelight(torch.autograd.Function):
             _lib.launch_count -= 1          # no derived-normal scatter
         ws.busy = False
         # gradients in the order of `params` (see forward_relight): VM factors, basis, [light_line], 3 x 6 MLP tensors
-        out = list(views) + [g_basis] + ([g_light] if g_light is not None else [])
+        out = list(views) + [r_basis] + ([r_light] if ll is not None else [])
         for head in ("renderModule", "renderModule_brdf", "renderModule_normal"):
-            out += mod_grads.get(head, [None] * 6)
+            out += [t[1] for t in mod_grads[head]] if head in mod_grads else [None] * 6
         return (None, None, None, None, None, None, None, None, *out)
 
 
