@@ -87,40 +87,59 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+    def __init__(self, gpu_index, period_ms=50):
+        self.rows, self.stamps, self.proc, self.idx, self.period = [], [], None, gpu_index, period_ms
+        self.begin = None
 
     def start(self):
+        """Spawn the sampler (idempotent).  Called BEFORE the warm-up steps so that nvidia-smi's own start-up (100+ ms,
+        longer than a 20-step timed region of this bench) is over when the timed region begins."""
+        if self.proc is not None:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.idx), "-lms", str(self.period)], stdout=subprocess.PIPE,
+                                         text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
+    def mark(self):
+        """The timed region starts now: rows that arrive from here on are the ones reported."""
+        self.start()
+        if self.begin is None:
+            self.begin = time.monotonic()
+
     def _read(self):
         for line in self.proc.stdout:
+            self.stamps.append(time.monotonic())
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        end = time.monotonic()
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace('.', '').isdigit())
-        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace('.', '').isdigit()]
+        self.t.join(timeout=2)
+        begin = self.begin if self.begin is not None else 0.0
+        inside = [r for r, ts in zip(self.rows, self.stamps) if begin <= ts <= end + 0.05]
+        # rows before mark() were taken during the warm-up steps (same load); used only if none fell inside
+        rows, window = (inside, "timed") if inside else (self.rows, "warmup+timed")
+        sm = sorted(float(r[1]) for r in rows if len(r) > 2 and r[1].replace('.', '').isdigit())
+        mx = [float(r[2]) for r in rows if len(r) > 2 and r[2].replace('.', '').isdigit()]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             for j, nm in enumerate(names):
                 if len(r) > 5 + j and r[5 + j].lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window, "period_ms": self.period}
 
 
 def dist_setup(n):
@@ -376,6 +395,8 @@ def measure(a, model, n_lights, rank, world, local, dev, scaling, with_e2e, cloc
 
     # ---- device-resident arm: inputs already in HBM when the timed region starts
     dev_batches = [(r.to(dev), l.to(dev)) for r, l in host_batches[:total]]
+    if clocks is not None:
+        clocks.start()
     for rays, li in dev_batches[:a.warmup]:
         step(rays, li)
     if graphed is not None:
@@ -384,7 +405,7 @@ def measure(a, model, n_lights, rank, world, local, dev, scaling, with_e2e, cloc
         graphed.reserve(4.0)
         sys.stderr.write(f"bench[{scaling}]: static lists {graphed.capacities()} after warm-up (seen {graphed._seen})\n")
     if clocks is not None:
-        clocks.start()
+        clocks.mark()
     events0 = (graphed.redone, graphed.recaptures) if graphed is not None else (0, 0)
     ms, cnt, launches = timed_region(dev_batches[a.warmup:], read_loss=False)
     out = {"scaling": scaling, "ms": ms, "cnt": cnt, "launches": launches, "per_rank": per_rank,
@@ -628,11 +649,13 @@ def run_relight_pass(a, rank, world, local, dev):
         return float(t.item()), ops.counters_dict(c)
 
     dev_chunks = [c.to(dev) for c in chunks[:total]]
-    for c in dev_chunks[:a.warmup]:
-        step(c, False)
     clocks = ClockSampler(local) if rank == 0 else None
     if clocks is not None:
         clocks.start()
+    for c in dev_chunks[:a.warmup]:
+        step(c, False)
+    if clocks is not None:
+        clocks.mark()
     ms, cnt = timed(dev_chunks[a.warmup:], False)
     for c in pinned[:a.warmup]:
         step(c, True)

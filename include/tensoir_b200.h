@@ -440,6 +440,23 @@ int tir_adam_step(const TirAdamTensor* table_dev, int32_t n_tensors, const int64
                   int64_t total_chunks, float* state_dev, float beta1, float beta2, float eps,
                   const float* found_inf_dev, int32_t clear_grad, void* stream);
 
+/* Total-variation regulariser of up to TIR_TV_MAX_PLANES VM planes in one launch: TVLoss (utils.py:143-162)
+ * as summed by TV_loss_density / TV_loss_app (tensoRF_rotated_lights.py:80-92).  x / grad: the storage of a [1,C,H,W]
+ * parameter, channel_last != 0: [H][W][C], else [C][H][W].
+ *   tir_tv_loss:     out[0] = sum_planes scale_h * sum (x[h+1]-x[h])^2 + scale_w * sum (x[w+1]-x[w])^2   (out is overwritten)
+ *   tir_tv_loss_bwd: grad += gout[0] * d out / d x      (gout in device memory: the weight decays every iteration)
+ * The caller folds 2 * TVLoss_weight * 1e-2 / count_h (count_w) into the scales. */
+#define TIR_TV_MAX_PLANES 3
+typedef struct TirTvPlane {
+  const float* x;
+  float* grad;                 /* only read by tir_tv_loss_bwd */
+  int32_t H, W, C;
+  int32_t channel_last;
+  float scale_h, scale_w;
+} TirTvPlane;
+int tir_tv_loss(const TirTvPlane* planes, int32_t n_planes, float* out, void* stream);
+int tir_tv_loss_bwd(const TirTvPlane* planes, int32_t n_planes, const float* gout, void* stream);
+
 /* On-the-fly ray generation from (view, pixel) ids instead of indexing a [n_views*H*W, 6] host table
  * (train_tensoIR.py:239-242): directions ((i+0.5-W/2)/f, (j+0.5-H/2)/f, 1) normalised and rotated by c2w[:3,:3], origin
  * c2w[:3,3] (dataLoader/ray_utils.py:25-43, :67-88).  c2w [n_views,4,4] row-major, pix = j*W + i -> rays [n,6]. */

@@ -58,6 +58,14 @@ class TirAdamTensor(C.Structure):
                 ("lr_dev", C.c_void_p), ("lr", C.c_float), ("l1", C.c_float)]
 
 
+class TirTvPlane(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("grad", C.c_void_p), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32),
+                ("channel_last", C.c_int32), ("scale_h", C.c_float), ("scale_w", C.c_float)]
+
+
+TV_MAX_PLANES = 3      # TIR_TV_MAX_PLANES
+
+
 class TirRayMaps(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("rgb", "depth", "normal", "albedo", "rough", "fresnel", "nd", "no")]
 
@@ -136,6 +144,8 @@ EXPORTS = {
                                 C.c_int32, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, C.c_void_p]),
     "tir_generate_rays": (C.c_int, [f32p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_float, f32p,
                                     C.c_void_p]),
+    "tir_tv_loss": (C.c_int, [C.c_void_p, C.c_int32, f32p, C.c_void_p]),
+    "tir_tv_loss_bwd": (C.c_int, [C.c_void_p, C.c_int32, f32p, C.c_void_p]),
     "tir_adam_chunk_elems": (C.c_int, []),
     "tir_adam_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_float, C.c_float, C.c_float,
                                 C.c_void_p, C.c_int32, C.c_void_p]),
@@ -188,7 +198,7 @@ KERNELS_PER_CALL = {"tir_pack_channels_last": 1, "tir_unpack_channels_last_add":
                     "tir_shade_fwd": 1, "tir_shade_bwd": 1, "tir_app_mlp_points": 1, "tir_app_mlp_points_save": 1, "tir_vm_app_products": 1, "tir_vm_app_products_bwd": 1,
                     "tir_vm_density_bwd": 1, "tir_vm_density_grad": 1, "tir_vm_density_grad_bwd": 1,
                     "tir_valid_samples_count": 1, "tir_valid_samples_fill": 1, "tir_composite_fwd": 1,
-                    "tir_adam_step": 2, "tir_generate_rays": 1, "tir_hits_prepare": 1, "tir_shade_hits_fwd": 1, "tir_shade_hits_bwd": 1,
+                    "tir_adam_step": 2, "tir_tv_loss": 1, "tir_tv_loss_bwd": 1, "tir_generate_rays": 1, "tir_hits_prepare": 1, "tir_shade_hits_fwd": 1, "tir_shade_hits_bwd": 1,
                     "tir_primary_march": 6, "tir_primary_app_list": 1, "tir_primary_heads": 5,
                     "tir_primary_backward": 9,
                     "tir_composite_bwd": 1, "tir_tail_fwd": 1, "tir_tail_bwd": 1, "tir_epilogue_fwd": 1,

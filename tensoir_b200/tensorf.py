@@ -9,7 +9,7 @@ from __future__ import annotations
 import torch
 import torch.nn.functional as F
 
-from . import vm_autograd
+from . import tv, vm_autograd
 from .tensorbase import TensorBase, AlphaGridMask, raw2alpha  # noqa: F401  (re-exported like the reference)
 
 
@@ -83,10 +83,12 @@ class TensorVMSplit(TensorBase):
         return sum(p.abs().mean() + l.abs().mean() for p, l in zip(self.density_plane, self.density_line))
 
     def TV_loss_density(self, reg):
-        return sum(reg(p) * 1e-2 for p in self.density_plane)
+        """tensoRF_rotated_lights.py:80-85; one kernel launch per direction of autograd (tv.py)."""
+        return tv.tv_planes(self.density_plane, reg, 1e-2, self.__dict__.get("_tir_grad_inplace", True))
 
     def TV_loss_app(self, reg):
-        return sum(reg(p) * 1e-2 for p in self.app_plane)
+        """tensoRF_rotated_lights.py:87-92."""
+        return tv.tv_planes(self.app_plane, reg, 1e-2, self.__dict__.get("_tir_grad_inplace", True))
 
     # ---- VM gathers (kernel-backed, differentiable w.r.t. the factors) -------------------
     def compute_densityfeature(self, xyz_sampled):

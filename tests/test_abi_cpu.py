@@ -41,18 +41,24 @@ def test_primary_struct_sizes_match_the_c_compiler(lib, tmp_path):
     import subprocess
     from tensoir_b200 import _lib
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "tensoir_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include "tensoir_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    'sizeof(TirHeadJob),sizeof(TirPrimaryWork),sizeof(TirPrimaryBwdWork),sizeof(TirPrimaryGrads),'
-                   'sizeof(TirField),sizeof(TirMlp));return 0;}\n')
+                   'sizeof(TirField),sizeof(TirMlp),sizeof(TirTvPlane),sizeof(TirAdamTensor));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(REPO, "include"), str(src), "-o", str(exe)], check=True)
     got = tuple(int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split())
     want = tuple(ctypes.sizeof(t) for t in (_lib.TirHeadJob, _lib.TirPrimaryWork, _lib.TirPrimaryBwdWork,
-                                            _lib.TirPrimaryGrads, _lib.TirField, _lib.TirMlp))
+                                            _lib.TirPrimaryGrads, _lib.TirField, _lib.TirMlp, _lib.TirTvPlane,
+                                            _lib.TirAdamTensor))
     assert got == want
 
 
 def test_null_arguments_are_rejected(lib):
+    assert lib.tir_tv_loss(None, 1, None, None) == -1
+    tab = (__import__("tensoir_b200")._lib.TirTvPlane * 1)()
+    assert lib.tir_tv_loss_bwd(tab, 4, None, None) == -1           # no gout
+    assert lib.tir_tv_loss(tab, 4, ctypes.c_void_p(16), None) == -2   # more planes than TIR_TV_MAX_PLANES
+    assert lib.tir_tv_loss(tab, 1, ctypes.c_void_p(16), None) == -1   # plane without storage
     assert lib.tir_pack_channels_last(None, None, 1, 1, 1, None) == -1
     assert lib.tir_density_points(None, None, 5, None, None, None) == -1
     assert lib.tir_tail_fwd(5, None, None, None, None, None, None, None, None, None, None) == -1
@@ -239,3 +245,30 @@ def test_channel_last_parameters_need_no_shadow(golden_rotated):
     bucket = GradBucket(m.parameters())
     for p, v in zip(bucket.params, bucket.views):
         assert v.shape == p.shape and v.stride() == p.stride()
+
+
+def test_tv_planes_host_logic():
+    """tv.tv_planes on CPU parameters: the reference's TVLoss module is simply called (the kernel is for CUDA planes),
+    and the per-plane scales handed to the kernel are 2 * weight * 1e-2 / count."""
+    from tensoir_b200 import tv
+
+    class TVLoss(torch.nn.Module):          # utils.py:143-162, restated
+        TVLoss_weight = 3.0
+
+        def forward(self, x):
+            b, _, h, w = x.shape
+            ch, cw = x[:, :, 1:, :].numel() // b, x[:, :, :, 1:].numel() // b
+            return self.TVLoss_weight * 2 * (torch.pow(x[:, :, 1:, :] - x[:, :, :h - 1, :], 2).sum() / ch
+                                             + torch.pow(x[:, :, :, 1:] - x[:, :, :, :w - 1], 2).sum() / cw) / b
+    ps = [torch.nn.Parameter(torch.randn(1, 8, 5, 7).contiguous(memory_format=torch.channels_last)),
+          torch.nn.Parameter(torch.randn(1, 8, 6, 4))]
+    reg = TVLoss()
+    v = tv.tv_planes(ps, reg, 1e-2)
+    assert torch.allclose(v, sum(reg(p) * 1e-2 for p in ps))
+    v.backward()
+    assert ps[0].grad is not None and ps[1].grad is not None
+    tab = tv._table([p.detach() for p in ps], 3.0 * 1e-2, None)
+    assert (tab[0].H, tab[0].W, tab[0].C, tab[0].channel_last) == (5, 7, 8, 1)
+    assert (tab[1].H, tab[1].W, tab[1].C, tab[1].channel_last) == (6, 4, 8, 0)
+    assert abs(tab[0].scale_h - 2 * 3.0e-2 / (8 * 4 * 7)) < 1e-9 and abs(tab[0].scale_w - 2 * 3.0e-2 / (8 * 5 * 6)) < 1e-9
+    assert tv._layout(torch.zeros(1, 4, 3, 3)[:, :, ::2]) is None

@@ -78,3 +78,33 @@ def test_configargparse_stand_in_reads_reference_configs(tmp_path):
                    "white_bkgd = 1\nunknown_key = 3\n")
     a = p.parse_args(["--config", str(cfg), "--n_iters", "24"])
     assert (a.expname, a.n_iters, a.upsamp_list, a.light_rotation, a.white_bkgd) == ("run", 24, [10000, 20000], ["000"], True)
+
+
+def test_clock_sampler_reports_rows_of_the_timed_region(tmp_path, monkeypatch):
+    """ClockSampler against a stand-in nvidia-smi with a 200 ms start-up: started before the warm-up, only rows that arrive
+    after mark() are reported ("window": "timed"); a throttle reason is picked up; without nvidia-smi it says so."""
+    import importlib
+    import stat
+    import time
+    stub = tmp_path / "nvidia-smi"
+    stub.write_text("#!" + sys.executable + "\nimport sys, time\nper = int(sys.argv[sys.argv.index('-lms') + 1]) / 1000\n"
+                    "time.sleep(0.2)\nk = 0\nwhile True:\n"
+                    "    clk = 1200 if k < 2 else 1965\n    k += 1\n"
+                    "    print(f'0, {clk}, 1965, 512.3, 0x4, Not Active, Not Active, Not Active, Active', flush=True)\n"
+                    "    time.sleep(per)\n")
+    stub.chmod(stub.stat().st_mode | stat.S_IEXEC)
+    monkeypatch.setenv("PATH", str(tmp_path) + os.pathsep + os.environ["PATH"])
+    sys.argv = ["bench.py"]
+    bench = importlib.import_module("bench")
+    c = bench.ClockSampler(0)
+    c.start()
+    time.sleep(0.45)                      # "warm-up": the start-up and the two low-clock rows fall in here
+    c.mark()
+    time.sleep(0.2)                       # "timed region"
+    out = c.stop()
+    assert out["window"] == "timed" and out["samples"] >= 2
+    assert out["sm_mhz"] == 1965.0 and out["sm_max_mhz"] == 1965.0 and out["reasons"] == ["sw_power_cap"]
+    monkeypatch.setenv("PATH", str(tmp_path / "nowhere"))
+    c = bench.ClockSampler(0)
+    c.mark()
+    assert c.stop()["reasons"] == ["nvidia-smi unavailable"]

@@ -999,3 +999,69 @@ def test_device_ray_generation_matches_host_rays():
     assert torch.equal(got[:, :3], want[:, :3])
     assert float((got[:, 3:] - want[:, 3:]).abs().max()) < 3e-7
     assert float((got[:, 3:].norm(dim=-1) - 1).abs().max()) < 1e-6
+
+
+class _TVLoss(torch.nn.Module):
+    """utils.TVLoss (utils.py:143-162), restated for the test."""
+
+    def __init__(self, TVLoss_weight=1):
+        super().__init__()
+        self.TVLoss_weight = TVLoss_weight
+
+    def forward(self, x):
+        b, _, h, w = x.shape
+        ch, cw = x[:, :, 1:, :].numel() // b, x[:, :, :, 1:].numel() // b
+        return self.TVLoss_weight * 2 * (torch.pow(x[:, :, 1:, :] - x[:, :, :h - 1, :], 2).sum() / ch
+                                         + torch.pow(x[:, :, :, 1:] - x[:, :, :, :w - 1], 2).sum() / cw) / b
+
+
+def test_fused_tv_matches_torch_autograd(golden_rotated):
+    """tv.tv_planes (one forward + one backward launch for the three planes) against autograd of the reference's TVLoss
+    expression: channel-last parameters (16 / 48 / 6 channels -> vector and scalar kernels), plain NCHW tensors, a decayed
+    loss weight, gradients handed to autograd and accumulated in place into an existing .grad."""
+    from tensoir_b200 import tv, _lib
+    g = torch.Generator().manual_seed(11)
+    reg = _TVLoss(1.7)
+
+    def planes(shapes, channel_last):
+        out = []
+        for sh in shapes:
+            t = torch.randn(sh, generator=g).to(DEV)
+            if channel_last:
+                t = t.contiguous(memory_format=torch.channels_last)
+            out.append(torch.nn.Parameter(t))
+        return out
+    cases = [([(1, 16, 37, 29), (1, 16, 29, 41), (1, 16, 41, 37)], True),
+             ([(1, 48, 21, 19), (1, 48, 19, 23), (1, 48, 23, 21)], True),
+             ([(1, 6, 9, 7), (1, 6, 7, 5)], True),
+             ([(1, 16, 13, 11), (1, 5, 8, 9), (1, 4, 6, 7)], False)]
+    for shapes, cl in cases:
+        ps = planes(shapes, cl)
+        qs = [torch.nn.Parameter(p.detach().clone(memory_format=torch.preserve_format)) for p in ps]
+        w = 0.05 * 0.9993
+        before = _lib.launch_count
+        ours = tv.tv_planes(ps, reg, 1e-2, inplace=False) * w
+        assert _lib.launch_count - before == 1
+        ref = sum(reg(q) * 1e-2 for q in qs) * w
+        assert abs(float(ours) - float(ref)) < 1e-5 * abs(float(ref)), (float(ours), float(ref))
+        ours.backward()
+        ref.backward()
+        assert _lib.launch_count - before == 2
+        for p, q in zip(ps, qs):
+            scale = float(q.grad.abs().max())
+            assert float((p.grad - q.grad).abs().max()) < 1e-5 * scale, (shapes, cl)
+        # second pass: .grad exists -> accumulated in place (no buffer handed to autograd), twice the gradient
+        held = [p.grad for p in ps]
+        (tv.tv_planes(ps, reg, 1e-2, inplace=True) * w).backward()
+        for p, q, h in zip(ps, qs, held):
+            assert p.grad is h
+            assert float((p.grad - 2 * q.grad).abs().max()) < 2e-5 * float(q.grad.abs().max())
+    # the model methods route through it (density: 3 planes in one launch) and keep the reference's values
+    m = model_from_fixture(golden_rotated, DEV)
+    before = _lib.launch_count
+    val = m.TV_loss_density(reg) + m.TV_loss_app(reg)
+    assert _lib.launch_count - before == 2
+    want = sum(reg(p) * 1e-2 for p in m.density_plane) + sum(reg(p) * 1e-2 for p in m.app_plane)
+    assert abs(float(val) - float(want)) < 1e-5 * abs(float(want))
+    # a callable that is not the reference's TVLoss is simply called
+    assert torch.allclose(m.TV_loss_density(lambda x: x.abs().mean()), sum(p.abs().mean() * 1e-2 for p in m.density_plane))
