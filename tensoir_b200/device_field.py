@@ -14,9 +14,6 @@ Updates made outside torch.optim and without version bumps must be announced wit
 """
 from __future__ import annotations
 
-import ctypes as C
-from typing import Optional
-
 import torch
 
 from . import _lib

@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import torch
 
-from .relight_utils import render_hits, render_with_BRDF
+from .relight_utils import render_hits, render_with_BRDF  # noqa: F401  (renderer.py:6 star-imports it too)
 
 
 def Renderer_TensoIR_train(rays=None, normal_gt=None, light_idx=None, tensoIR=None, N_samples=-1, ndc_ray=False,

@@ -2,8 +2,6 @@
 equation at the surface points, models/relight_utils.py:452-475, forward and analytic backward."""
 from __future__ import annotations
 
-import ctypes as C
-
 import torch
 
 from . import _lib

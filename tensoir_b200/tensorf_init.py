@@ -5,7 +5,7 @@ from __future__ import annotations
 import torch
 
 from . import primary, vm_autograd
-from .tensorbase import TensorBase, MLPRender_Fea
+from .tensorbase import MLPRender_Fea
 from .tensorf import TensorVMSplit as _RelightVMSplit
 
 

@@ -9,8 +9,6 @@ parameter's layout, like primary_fused does).
 """
 from __future__ import annotations
 
-import ctypes as C
-
 import torch
 
 from . import _lib

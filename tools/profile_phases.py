@@ -1,6 +1,6 @@
 """Per-phase GPU time of the (eager, shape-static) training step: forward phases by record_function range, backward
 by autograd node."""
-import os, sys, re, collections, torch
+import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import bench
